@@ -1,0 +1,313 @@
+// allreduce.cu — all-reduce kernels and their dispatcher.
+//
+// Three algorithms, all in ONE launch each (stage-in, cross-GPU barrier, reduce,
+// barrier, stage-out are phases of the same persistent grid):
+//
+//   one-shot : every rank stages its input in its own symmetric slot, then reads
+//              all n staged inputs over NVLink and reduces rank-ascending.  One
+//              barrier; latency path for small messages.
+//   two-shot : the message is cut into rows of n*512 16-byte units; rank r owns
+//              units [r*512,(r+1)*512) of every row.  The owner loads its units
+//              from all n peers' HBM (rank-ascending reduction), and pushes the
+//              result back into all n peers' slots.  Every element is read and
+//              written by exactly one thread system-wide, so the reduce-scatter
+//              and all-gather halves fuse without a barrier between them.
+//   NVLS     : same ownership, but the n loads are one multimem.ld_reduce and the
+//              n stores one multimem.st on the NVSwitch multicast alias.
+//
+// CTA b of every rank works on the same rows in every phase, so a barrier between
+// CTA b's of all ranks (flags in the signal pad) is the only synchronisation needed:
+// no grid-wide sync, no host involvement.
+#include "kernel_utils.cuh"
+
+namespace b200 {
+
+struct ARArgs {
+  const char *in;
+  char *out;
+  size_t nbytes;
+  size_t staging_bytes;
+  long long sym_off;  // >= 0: operand lives in the symmetric data region at this offset
+                      //       (zero-copy, in place); < 0: stage through the rotating slot
+};
+
+// ---------------------------------------------------------------------------
+// one-shot
+// ---------------------------------------------------------------------------
+template <typename T, int OP>
+__global__ void __launch_bounds__(kThreads, 1) allreduce_oneshot_kernel(DevComm c, ARArgs a) {
+  using Tr = Traits<T>;
+  const uint32_t launch = c.st->launch_ctr;
+  const uint32_t ep = launch * 4u;
+  const int n = c.world, r = c.rank;
+  const Units un = make_units(a.nbytes);
+  const size_t U = un.total();
+  const bool in_al = is_aligned16(a.in), out_al = is_aligned16(a.out);
+  const size_t off = staging_slot_offset(launch, a.staging_bytes);
+  const size_t stride = size_t(gridDim.x) * kThreads;
+  const size_t first = size_t(blockIdx.x) * kThreads + threadIdx.x;
+
+  char *mine = c.data[r] + off;
+  for (size_t u = first; u < U; u += stride) st_vec(mine + (u << 4), load_user_unit(a.in, u, un, in_al));
+
+  if (!cta_barrier_all(c, ep + 1)) {
+    finish_launch(c);
+    return;
+  }
+
+  for (size_t u = first; u < U; u += stride) {
+    uint4 v[kMaxRanks];
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p)
+      if (p < n) v[p] = ld_peer(c.data[p] + off + (u << 4));
+    typename Tr::Acc acc = Tr::unpack(v[0]);
+#pragma unroll
+    for (int p = 1; p < kMaxRanks; ++p)
+      if (p < n) Tr::template reduce<OP>(acc, Tr::unpack(v[p]));
+    if (OP == B200_AVG) Tr::average(acc, n);
+    store_user_unit(a.out, u, un, out_al, Tr::pack(acc));
+  }
+  finish_launch(c);
+}
+
+// ---------------------------------------------------------------------------
+// two-shot / NVLS
+// ---------------------------------------------------------------------------
+template <typename T, int OP, bool NVLS>
+__global__ void __launch_bounds__(kThreads, 1) allreduce_twoshot_kernel(DevComm c, ARArgs a) {
+  using Tr = Traits<T>;
+  const uint32_t launch = c.st->launch_ctr;
+  const uint32_t ep = launch * 4u;
+  const int n = c.world, r = c.rank;
+  const int t = threadIdx.x;
+  const Units un = make_units(a.nbytes);
+  const size_t U = un.total();
+  const size_t row_units = size_t(n) * kThreads;
+  const size_t R = (U + row_units - 1) / row_units;
+  const bool staged = a.sym_off < 0;
+  const size_t off = staged ? staging_slot_offset(launch, a.staging_bytes) : size_t(a.sym_off);
+  const size_t G = gridDim.x;
+
+  // ---- phase 0: stage this CTA's rows into the local symmetric slot -------------
+  if (staged) {
+    const bool in_al = is_aligned16(a.in);
+    char *mine = c.data[r] + off;
+    for (size_t row = blockIdx.x; row < R; row += G) {
+      uint4 v[kMaxRanks];
+      const size_t base = row * row_units + t;
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; ++k) {
+        const size_t u = base + size_t(k) * kThreads;
+        if (k < n && u < U) v[k] = load_user_unit(a.in, u, un, in_al);
+      }
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; ++k) {
+        const size_t u = base + size_t(k) * kThreads;
+        if (k < n && u < U) st_vec(mine + (u << 4), v[k]);
+      }
+    }
+  }
+
+  if (!cta_barrier_all(c, ep + 1)) {
+    finish_launch(c);
+    return;
+  }
+
+  // ---- phase 1: reduce the units this rank owns, publish to every peer ------------
+  if (NVLS) {
+    constexpr int UNR = 4;
+    char *mc = c.mc_data + off;
+    for (size_t row0 = blockIdx.x; row0 < R; row0 += G * UNR) {
+      uint4 v[UNR];
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        const size_t row = row0 + size_t(j) * G;
+        const size_t u = row * row_units + size_t(r) * kThreads + t;
+        if (row < R && u < U) v[j] = Multimem<T>::ld_reduce_sum(mc + (u << 4));
+      }
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        const size_t row = row0 + size_t(j) * G;
+        const size_t u = row * row_units + size_t(r) * kThreads + t;
+        if (row < R && u < U) {
+          if (OP == B200_AVG) {
+            typename Tr::Acc acc = Tr::unpack(v[j]);
+            Tr::average(acc, n);
+            v[j] = Tr::pack(acc);
+          }
+          multimem_st(mc + (u << 4), v[j]);
+        }
+      }
+    }
+  } else {
+    constexpr int UNR = 2;
+    for (size_t row0 = blockIdx.x; row0 < R; row0 += G * UNR) {
+      uint4 v[UNR][kMaxRanks];
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        const size_t row = row0 + size_t(j) * G;
+        const size_t u = row * row_units + size_t(r) * kThreads + t;
+        if (row < R && u < U) {
+#pragma unroll
+          for (int p = 0; p < kMaxRanks; ++p)
+            if (p < n) v[j][p] = ld_peer(c.data[p] + off + (u << 4));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        const size_t row = row0 + size_t(j) * G;
+        const size_t u = row * row_units + size_t(r) * kThreads + t;
+        if (row < R && u < U) {
+          typename Tr::Acc acc = Tr::unpack(v[j][0]);
+#pragma unroll
+          for (int p = 1; p < kMaxRanks; ++p)
+            if (p < n) Tr::template reduce<OP>(acc, Tr::unpack(v[j][p]));
+          if (OP == B200_AVG) Tr::average(acc, n);
+          const uint4 res = Tr::pack(acc);
+#pragma unroll
+          for (int i = 0; i < kMaxRanks; ++i) {
+            if (i < n) {
+              int p = r + i;  // start with the local copy, then walk the peers
+              if (p >= n) p -= n;
+              st_vec(c.data[p] + off + (u << 4), res);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  if (!cta_barrier_all(c, ep + 2)) {
+    finish_launch(c);
+    return;
+  }
+
+  // ---- phase 2: copy this CTA's rows out of the local slot ------------------------
+  if (staged) {
+    const bool out_al = is_aligned16(a.out);
+    const char *mine = c.data[r] + off;
+    for (size_t row = blockIdx.x; row < R; row += G) {
+      uint4 v[kMaxRanks];
+      const size_t base = row * row_units + t;
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; ++k) {
+        const size_t u = base + size_t(k) * kThreads;
+        if (k < n && u < U) v[k] = ld_peer(mine + (u << 4));
+      }
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; ++k) {
+        const size_t u = base + size_t(k) * kThreads;
+        if (k < n && u < U) store_user_unit(a.out, u, un, out_al, v[k]);
+      }
+    }
+  }
+  finish_launch(c);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+template <typename T, int OP>
+static int launch_allreduce(b200_comm *c, const char *in, char *out, size_t nbytes, int algo,
+                            long long sym_off, cudaStream_t stream) {
+  DevComm dc = c->dev();
+  ARArgs a{in, out, nbytes, c->staging_bytes, sym_off};
+  const size_t U = make_units(nbytes).total();
+  if (algo == B200_ALGO_ONESHOT) {
+    a.sym_off = -1;
+    int g = pick_blocks(c, (U + kThreads - 1) / kThreads, 32);
+    allreduce_oneshot_kernel<T, OP><<<g, kThreads, 0, stream>>>(dc, a);
+  } else {
+    const size_t rows = (U + size_t(c->world) * kThreads - 1) / (size_t(c->world) * kThreads);
+    int g = pick_blocks(c, rows, c->sm_count);
+    if (algo == B200_ALGO_NVLS) {
+      if constexpr (Multimem<T>::kSum && (OP == B200_SUM || OP == B200_AVG)) {
+        allreduce_twoshot_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(dc, a);
+      } else {
+        set_error("NVLS all-reduce supports SUM/AVG on f32/f16/bf16 only");
+        return B200_ERR_UNSUPPORTED;
+      }
+    } else {
+      allreduce_twoshot_kernel<T, OP, false><<<g, kThreads, 0, stream>>>(dc, a);
+    }
+  }
+  B200_LAUNCH_CHECK(c);
+  return B200_OK;
+}
+
+static bool nvls_capable(int dtype, int op) {
+  return (dtype == B200_F32 || dtype == B200_F16 || dtype == B200_BF16) &&
+         (op == B200_SUM || op == B200_AVG);
+}
+
+static size_t oneshot_limit(const b200_comm *c) {
+  static long long env = [] {
+    const char *s = getenv("B200_ONESHOT_MAX_BYTES");
+    return s ? atoll(s) : -1ll;
+  }();
+  if (env >= 0) return size_t(env);
+  // each rank reads world * nbytes in the one-shot scheme
+  return (size_t(1) << 20) / size_t(c->world);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_allreduce(b200_comm_t c, const void *in, void *out, size_t count, int dtype,
+                              int op, int algo, void *stream_) {
+  int rc = check_usable(c);
+  if (rc) return rc;
+  const size_t es = b200_dtype_size(dtype);
+  if (es == 0) {
+    set_error("unsupported dtype %d", dtype);
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (op < 0 || op >= B200_OP_COUNT) {
+    set_error("unsupported reduce op %d", op);
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (count == 0) return B200_OK;
+  if (!in || !out) {
+    set_error("null tensor pointer");
+    return B200_ERR_INVALID;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200_CHECK_CUDA(cudaSetDevice(c->device));
+  const size_t total = count * es;
+  if (c->world == 1) {
+    if (in != out) B200_CHECK_CUDA(cudaMemcpyAsync(out, in, total, cudaMemcpyDeviceToDevice, stream));
+    return B200_OK;
+  }
+  if (algo == B200_ALGO_NVLS && !c->mc_active) {
+    set_error("NVLS requested but the multicast mapping is not active");
+    return B200_ERR_UNSUPPORTED;
+  }
+
+  // zero-copy when the operand sits in the symmetric heap (and is updated in place)
+  long long sym_off = -1;
+  if (in == out && b200_symm_contains(c, in, total) && is_aligned16(in))
+    sym_off = static_cast<const char *>(in) - reinterpret_cast<const char *>(c->data.va[c->rank]);
+
+  const char *src = static_cast<const char *>(in);
+  char *dst = static_cast<char *>(out);
+  // Messages larger than one staging slot are processed slot by slot.
+  const size_t chunk_max = sym_off >= 0 ? total : c->staging_bytes;
+  for (size_t done = 0; done < total;) {
+    const size_t nbytes = (total - done) < chunk_max ? (total - done) : chunk_max;
+    int a = algo;
+    if (a == B200_ALGO_AUTO) {
+      if (sym_off < 0 && nbytes <= oneshot_limit(c)) a = B200_ALGO_ONESHOT;
+      else if (c->mc_active && nvls_capable(dtype, op)) a = B200_ALGO_NVLS;
+      else a = B200_ALGO_TWOSHOT;
+    }
+    if (a == B200_ALGO_ONESHOT && nbytes > c->staging_bytes) a = B200_ALGO_TWOSHOT;
+    const long long so = sym_off >= 0 ? sym_off + (long long)done : -1;
+    B200_DISPATCH_DTYPE(dtype, T, B200_DISPATCH_OP(op, OP, {
+                          rc = launch_allreduce<T, OP>(c, src + done, dst + done, nbytes, a, so, stream);
+                        }));
+    if (rc) return rc;
+    done += nbytes;
+  }
+  return B200_OK;
+}

@@ -1,0 +1,312 @@
+// grad.cu — fused data-parallel gradient synchronisation.
+//
+// One launch per DDP bucket does what the reference path does in four to six kernels
+// (c10d reducer div_ / bf16_compress_hook casts + ncclAllReduce + cast back, reached
+// from train/torch/config.py:144 and train/torch/train_loop_utils.py:456-480):
+//
+//   stage-in : read the fp32 bucket, multiply by `scale` (1/world for DDP's mean),
+//              cast to the wire dtype, write to the symmetric slot
+//   reduce   : two-shot over peer HBM, or NVLS multimem.ld_reduce(.acc::f32)+multimem.st
+//   stage-out: read the reduced wire values, cast back to fp32, write the bucket
+//
+// With wire = bf16 the NVLink traffic and the staging traffic are halved.
+#include "kernel_utils.cuh"
+
+namespace b200 {
+
+struct GradArgs {
+  float *grad;
+  size_t count;
+  float scale;
+  size_t staging_bytes;
+};
+
+template <typename W>
+struct Wire;
+template <>
+struct Wire<float> {
+  static constexpr int kElems = 4;
+  static __device__ __forceinline__ uint4 pack(const float *f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+  static __device__ __forceinline__ void unpack(uint4 v, float *f) {
+    f[0] = __uint_as_float(v.x);
+    f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z);
+    f[3] = __uint_as_float(v.w);
+  }
+};
+template <>
+struct Wire<__nv_bfloat16> {
+  static constexpr int kElems = 8;
+  static __device__ __forceinline__ uint4 pack(const float *f) {
+    uint4 v;
+    __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+  }
+  static __device__ __forceinline__ void unpack(uint4 v, float *f) {
+    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(p[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+};
+template <>
+struct Wire<__half> {
+  static constexpr int kElems = 8;
+  static __device__ __forceinline__ uint4 pack(const float *f) {
+    uint4 v;
+    __half2 *p = reinterpret_cast<__half2 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+  }
+  static __device__ __forceinline__ void unpack(uint4 v, float *f) {
+    const __half2 *p = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __half22float2(p[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+};
+
+// wire unit u covers gradient elements [u*E, u*E+E)
+template <typename W>
+__device__ __forceinline__ uint4 load_grad_unit(const float *g, size_t u, size_t count, float scale, bool aligned) {
+  constexpr int E = Wire<W>::kElems;
+  float f[E];
+  const size_t e0 = u * E;
+  if (aligned && e0 + E <= count) {
+#pragma unroll
+    for (int k = 0; k < E / 4; ++k) {
+      const uint4 v = ld_stream(g + e0 + 4 * k);
+      f[4 * k + 0] = __uint_as_float(v.x);
+      f[4 * k + 1] = __uint_as_float(v.y);
+      f[4 * k + 2] = __uint_as_float(v.z);
+      f[4 * k + 3] = __uint_as_float(v.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < E; ++i) f[i] = (e0 + i < count) ? g[e0 + i] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < E; ++i) f[i] *= scale;
+  return Wire<W>::pack(f);
+}
+
+template <typename W>
+__device__ __forceinline__ void store_grad_unit(float *g, size_t u, size_t count, bool aligned, uint4 w) {
+  constexpr int E = Wire<W>::kElems;
+  float f[E];
+  Wire<W>::unpack(w, f);
+  const size_t e0 = u * E;
+  if (aligned && e0 + E <= count) {
+#pragma unroll
+    for (int k = 0; k < E / 4; ++k)
+      st_vec(g + e0 + 4 * k, make_uint4(__float_as_uint(f[4 * k]), __float_as_uint(f[4 * k + 1]),
+                                       __float_as_uint(f[4 * k + 2]), __float_as_uint(f[4 * k + 3])));
+  } else {
+#pragma unroll
+    for (int i = 0; i < E; ++i)
+      if (e0 + i < count) g[e0 + i] = f[i];
+  }
+}
+
+template <typename W, bool NVLS>
+__global__ void __launch_bounds__(kThreads, 1) grad_allreduce_kernel(DevComm c, GradArgs a) {
+  using Tr = Traits<W>;
+  constexpr int E = Wire<W>::kElems;
+  const uint32_t launch = c.st->launch_ctr;
+  const uint32_t ep = launch * 4u;
+  const int n = c.world, r = c.rank;
+  const int t = threadIdx.x;
+  const size_t U = (a.count + E - 1) / E;
+  const size_t row_units = size_t(n) * kThreads;
+  const size_t R = (U + row_units - 1) / row_units;
+  const size_t off = staging_slot_offset(launch, a.staging_bytes);
+  const size_t G = gridDim.x;
+  const bool al = is_aligned16(a.grad);
+  char *mine = c.data[r] + off;
+
+  for (size_t row = blockIdx.x; row < R; row += G) {
+    uint4 v[kMaxRanks];
+    const size_t base = row * row_units + t;
+#pragma unroll
+    for (int k = 0; k < kMaxRanks; ++k) {
+      const size_t u = base + size_t(k) * kThreads;
+      if (k < n && u < U) v[k] = load_grad_unit<W>(a.grad, u, a.count, a.scale, al);
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxRanks; ++k) {
+      const size_t u = base + size_t(k) * kThreads;
+      if (k < n && u < U) st_vec(mine + (u << 4), v[k]);
+    }
+  }
+
+  if (!cta_barrier_all(c, ep + 1)) {
+    finish_launch(c);
+    return;
+  }
+
+  if (NVLS) {
+    constexpr int UNR = 4;
+    char *mc = c.mc_data + off;
+    for (size_t row0 = blockIdx.x; row0 < R; row0 += G * UNR) {
+      uint4 v[UNR];
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        const size_t row = row0 + size_t(j) * G;
+        const size_t u = row * row_units + size_t(r) * kThreads + t;
+        if (row < R && u < U) v[j] = Multimem<W>::ld_reduce_sum(mc + (u << 4));
+      }
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        const size_t row = row0 + size_t(j) * G;
+        const size_t u = row * row_units + size_t(r) * kThreads + t;
+        if (row < R && u < U) multimem_st(mc + (u << 4), v[j]);
+      }
+    }
+  } else {
+    constexpr int UNR = 2;
+    for (size_t row0 = blockIdx.x; row0 < R; row0 += G * UNR) {
+      uint4 v[UNR][kMaxRanks];
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        const size_t row = row0 + size_t(j) * G;
+        const size_t u = row * row_units + size_t(r) * kThreads + t;
+        if (row < R && u < U) {
+#pragma unroll
+          for (int p = 0; p < kMaxRanks; ++p)
+            if (p < n) v[j][p] = ld_peer(c.data[p] + off + (u << 4));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        const size_t row = row0 + size_t(j) * G;
+        const size_t u = row * row_units + size_t(r) * kThreads + t;
+        if (row < R && u < U) {
+          typename Tr::Acc acc = Tr::unpack(v[j][0]);
+#pragma unroll
+          for (int p = 1; p < kMaxRanks; ++p)
+            if (p < n) Tr::template reduce<B200_SUM>(acc, Tr::unpack(v[j][p]));
+          const uint4 res = Tr::pack(acc);
+#pragma unroll
+          for (int i = 0; i < kMaxRanks; ++i) {
+            if (i < n) {
+              int p = r + i;
+              if (p >= n) p -= n;
+              st_vec(c.data[p] + off + (u << 4), res);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  if (!cta_barrier_all(c, ep + 2)) {
+    finish_launch(c);
+    return;
+  }
+
+  for (size_t row = blockIdx.x; row < R; row += G) {
+    uint4 v[kMaxRanks];
+    const size_t base = row * row_units + t;
+#pragma unroll
+    for (int k = 0; k < kMaxRanks; ++k) {
+      const size_t u = base + size_t(k) * kThreads;
+      if (k < n && u < U) v[k] = ld_peer(mine + (u << 4));
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxRanks; ++k) {
+      const size_t u = base + size_t(k) * kThreads;
+      if (k < n && u < U) store_grad_unit<W>(a.grad, u, a.count, al, v[k]);
+    }
+  }
+  finish_launch(c);
+}
+
+// world == 1: the same arithmetic without any peer (scale, round-trip through the wire type).
+template <typename W>
+__global__ void grad_local_kernel(GradArgs a) {
+  constexpr int E = Wire<W>::kElems;
+  const size_t U = (a.count + E - 1) / E;
+  const bool al = is_aligned16(a.grad);
+  for (size_t u = size_t(blockIdx.x) * blockDim.x + threadIdx.x; u < U; u += size_t(gridDim.x) * blockDim.x)
+    store_grad_unit<W>(a.grad, u, a.count, al, load_grad_unit<W>(a.grad, u, a.count, a.scale, al));
+}
+
+template <typename W>
+static int launch_grad(b200_comm *c, const GradArgs &a, cudaStream_t stream) {
+  constexpr int E = Wire<W>::kElems;
+  const size_t U = (a.count + E - 1) / E;
+  if (c->world == 1) {
+    int g = pick_blocks(c, (U + kThreads - 1) / kThreads, 4 * c->sm_count);
+    grad_local_kernel<W><<<g, kThreads, 0, stream>>>(a);
+    B200_LAUNCH_CHECK(c);
+    return B200_OK;
+  }
+  const size_t rows = (U + size_t(c->world) * kThreads - 1) / (size_t(c->world) * kThreads);
+  int g = pick_blocks(c, rows, c->sm_count);
+  if (c->mc_active) grad_allreduce_kernel<W, true><<<g, kThreads, 0, stream>>>(c->dev(), a);
+  else grad_allreduce_kernel<W, false><<<g, kThreads, 0, stream>>>(c->dev(), a);
+  B200_LAUNCH_CHECK(c);
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_grad_allreduce(b200_comm_t c, float *grad, size_t count, float scale,
+                                   int wire_dtype, void *stream_) {
+  int rc = check_usable(c);
+  if (rc) return rc;
+  if (wire_dtype != B200_F32 && wire_dtype != B200_BF16 && wire_dtype != B200_F16) {
+    set_error("wire dtype must be f32, bf16 or f16 (got %d)", wire_dtype);
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (count == 0) return B200_OK;
+  if (!grad) {
+    set_error("null gradient pointer");
+    return B200_ERR_INVALID;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200_CHECK_CUDA(cudaSetDevice(c->device));
+  const size_t wire_es = b200_dtype_size(wire_dtype);
+  // elements per launch so the wire image fits one staging slot (multiple of 8 elements)
+  const size_t chunk_elems = (c->staging_bytes / wire_es) & ~size_t(7);
+  for (size_t done = 0; done < count;) {
+    const size_t n = (count - done) < chunk_elems ? (count - done) : chunk_elems;
+    GradArgs a{grad + done, n, scale, c->staging_bytes};
+    if (wire_dtype == B200_F32) rc = launch_grad<float>(c, a, stream);
+    else if (wire_dtype == B200_BF16) rc = launch_grad<__nv_bfloat16>(c, a, stream);
+    else rc = launch_grad<__half>(c, a, stream);
+    if (rc) return rc;
+    done += n;
+  }
+  return B200_OK;
+}
+
+// Multi-tensor all-reduce: v1 issues one fused launch per tensor (no host-side flatten,
+// no extra device copies); see DESIGN.md for the planned single-launch table variant.
+extern "C" int b200_allreduce_multi(b200_comm_t c, void *const *ptrs, const size_t *counts,
+                                    int ntensors, int dtype, int op, void *stream) {
+  int rc = check_usable(c);
+  if (rc) return rc;
+  if (ntensors < 0 || (ntensors > 0 && (!ptrs || !counts))) {
+    set_error("invalid tensor list");
+    return B200_ERR_INVALID;
+  }
+  for (int i = 0; i < ntensors; ++i) {
+    rc = b200_allreduce(c, ptrs[i], ptrs[i], counts[i], dtype, op, B200_ALGO_AUTO, stream);
+    if (rc) return rc;
+  }
+  return B200_OK;
+}

@@ -1,0 +1,144 @@
+// p2p.cu — point-to-point send / recv (the transport under the Compiled-Graph
+// GPU channel and RDT's two-sided path).
+//
+// Sender-push over NVLink into the receiver's inbox, chunked through per-CTA rings:
+//
+//   receiver's inbox[src] = kP2PRings sub-rings x kP2PSlots chunks
+//   CTA b of the send kernel and CTA b of the recv kernel own sub-ring b.
+//
+//   send: wait until the slot was consumed (ack flag in the SENDER's signal pad),
+//         store the chunk into the peer inbox, release-store "ready = seq+1" into
+//         the RECEIVER's signal pad.
+//   recv: acquire-wait ready == seq+1, copy the chunk from local HBM into the
+//         caller's tensor, release-store "ack = seq+1" into the sender's pad.
+//
+// Sequence numbers persist in rank-local device memory, so messages of any size
+// interleave correctly and a send completes without the receiver having been
+// launched as long as the message fits the ring (eager protocol).
+#include "kernel_utils.cuh"
+
+namespace b200 {
+
+struct P2PArgs {
+  char *buf;
+  size_t nbytes;
+  int peer;
+};
+
+__device__ __forceinline__ bool cta_wait_flag(const DevComm &c, const uint32_t *flag, uint32_t target) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = wait_flag_ge(c, flag, target) ? 1 : 0;
+  __syncthreads();
+  return ok != 0;
+}
+
+template <bool SEND>
+__global__ void __launch_bounds__(kThreads, 1) p2p_kernel(DevComm c, P2PArgs a) {
+  const int me = c.rank, peer = a.peer;
+  const int b = blockIdx.x, G = gridDim.x;
+  const size_t ring_bytes = c.inbox_bytes / kP2PRings;
+  const size_t chunk = ring_bytes / kP2PSlots;
+  const size_t nchunks = (a.nbytes + chunk - 1) / chunk;
+  const bool al = is_aligned16(a.buf);
+
+  uint32_t *seq_word = SEND ? &c.st->send_seq[peer][b] : &c.st->recv_seq[peer][b];
+  uint32_t seq = *seq_word;
+
+  // sender: data lands in the peer's inbox[me]; receiver: reads its own inbox[peer]
+  char *ring = (SEND ? c.inbox[peer] + size_t(me) * c.inbox_bytes : c.inbox[me] + size_t(peer) * c.inbox_bytes) +
+               size_t(b) * ring_bytes;
+  // ready flags live in the receiver's pad, ack flags in the sender's pad
+  uint32_t *ready = (SEND ? c.sig[peer] + kSigP2PReady + (size_t(me) * kP2PRings + b) * kP2PSlots
+                          : c.sig[me] + kSigP2PReady + (size_t(peer) * kP2PRings + b) * kP2PSlots);
+  uint32_t *ack = (SEND ? c.sig[me] + kSigP2PAck + size_t(peer) * kP2PRings + b
+                        : c.sig[peer] + kSigP2PAck + size_t(me) * kP2PRings + b);
+
+  for (size_t j = b; j < nchunks; j += G) {
+    const size_t lo = j * chunk;
+    const size_t len = (a.nbytes - lo) < chunk ? (a.nbytes - lo) : chunk;
+    const Units un = make_units(len);
+    const size_t U = un.total();
+    const uint32_t slot = seq % kP2PSlots;
+    char *slot_ptr = ring + size_t(slot) * chunk;
+    char *user = a.buf + lo;
+    if (SEND) {
+      // slot free once the receiver consumed chunk (seq - kP2PSlots)
+      if (!cta_wait_flag(c, ack, seq + 1u - kP2PSlots)) break;
+      for (size_t u0 = threadIdx.x; u0 < U; u0 += size_t(kThreads) * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const size_t u = u0 + size_t(k) * kThreads;
+          if (u < U) v[k] = load_user_unit(user, u, un, al);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const size_t u = u0 + size_t(k) * kThreads;
+          if (u < U) st_vec(slot_ptr + (u << 4), v[k]);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_sys(ready + slot, seq + 1u);
+    } else {
+      if (!cta_wait_flag(c, ready + slot, seq + 1u)) break;
+      for (size_t u0 = threadIdx.x; u0 < U; u0 += size_t(kThreads) * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const size_t u = u0 + size_t(k) * kThreads;
+          if (u < U) v[k] = ld_peer(slot_ptr + (u << 4));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const size_t u = u0 + size_t(k) * kThreads;
+          if (u < U) store_user_unit(user, u, un, al, v[k]);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_sys(ack, seq + 1u);
+    }
+    ++seq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *seq_word = seq;
+}
+
+static int p2p_common(b200_comm *c, void *buf, size_t nbytes, int peer, cudaStream_t stream, bool send) {
+  int rc = check_usable(c);
+  if (rc) return rc;
+  if (peer < 0 || peer >= c->world) {
+    set_error("peer rank %d out of range for world size %d", peer, c->world);
+    return B200_ERR_INVALID;
+  }
+  if (peer == c->rank) {
+    set_error("peer rank %d is this rank", peer);
+    return B200_ERR_INVALID;
+  }
+  if (nbytes == 0) return B200_OK;
+  if (!buf) {
+    set_error("null tensor pointer");
+    return B200_ERR_INVALID;
+  }
+  B200_CHECK_CUDA(cudaSetDevice(c->device));
+  const size_t chunk = c->inbox_bytes / kP2PRings / kP2PSlots;
+  const size_t nchunks = (nbytes + chunk - 1) / chunk;
+  // Grid is a pure function of the message size so both sides pair CTA b with CTA b.
+  int g = int(nchunks < size_t(kP2PRings) ? nchunks : size_t(kP2PRings));
+  P2PArgs a{static_cast<char *>(buf), nbytes, peer};
+  if (send) p2p_kernel<true><<<g, kThreads, 0, stream>>>(c->dev(), a);
+  else p2p_kernel<false><<<g, kThreads, 0, stream>>>(c->dev(), a);
+  B200_LAUNCH_CHECK(c);
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_send(b200_comm_t c, const void *buf, size_t nbytes, int peer, void *stream) {
+  return p2p_common(c, const_cast<void *>(buf), nbytes, peer, static_cast<cudaStream_t>(stream), true);
+}
+
+extern "C" int b200_recv(b200_comm_t c, void *buf, size_t nbytes, int peer, void *stream) {
+  return p2p_common(c, buf, nbytes, peer, static_cast<cudaStream_t>(stream), false);
+}
