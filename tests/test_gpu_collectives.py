@@ -1,0 +1,419 @@
+"""GPU parity tests: the CUDA kernels (through the C ABI) against the oracle and the golden
+fixtures generated from the reference.  Integer / index work must be bit exact; fp32 sums on
+the peer-load paths are bit exact against the rank-ascending oracle and within
+1e-6 * sum_r |x_r| of the reference's gloo output; NVLS sums meet the tolerance criterion.
+
+Runs on a single GPU (ranks share the device) and on multi-GPU boxes (one device per rank).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import collective_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+try:
+    import ml_dtypes
+
+    BF16 = np.dtype(ml_dtypes.bfloat16)
+except Exception:  # pragma: no cover
+    BF16 = None
+
+TORCH_DT = {"uint8": torch.uint8, "int8": torch.int8, "int32": torch.int32, "int64": torch.int64,
+            "float16": torch.float16, "bfloat16": torch.bfloat16, "float32": torch.float32,
+            "float64": torch.float64}
+OPS = {"SUM": 0, "PRODUCT": 1, "MIN": 2, "MAX": 3}
+WORLDS = [2, 3, 4, 8]
+
+
+def _np_view(a, dname):
+    return a.view(BF16) if dname == "bfloat16" else a
+
+
+def _to_dev(a: np.ndarray, dname: str, device) -> torch.Tensor:
+    if dname == "bfloat16":
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint16).copy()).view(torch.bfloat16).to(device)
+    return torch.from_numpy(np.ascontiguousarray(a).copy()).to(device)
+
+
+def _to_np(t: torch.Tensor, dname: str) -> np.ndarray:
+    if dname == "bfloat16":
+        return t.cpu().view(torch.uint16).numpy().view(BF16)
+    return t.cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def groups(native_lib):
+    from ray_b200.testing import LocalGroup
+
+    cache = {}
+
+    def get(n):
+        if n not in cache:
+            cache[n] = LocalGroup(n, timeout_ms=15000, staging_bytes=8 << 20, heap_bytes=8 << 20,
+                                  inbox_bytes=2 << 20)
+        return cache[n]
+
+    yield get
+    for g in cache.values():
+        g.destroy()
+
+
+def _algos(g):
+    from ray_b200 import _native as N
+
+    out = [("oneshot", N.ALGO_ONESHOT), ("twoshot", N.ALGO_TWOSHOT), ("auto", N.ALGO_AUTO)]
+    if g.has_multicast:
+        out.append(("nvls", N.ALGO_NVLS))
+    return out
+
+
+@pytest.mark.parametrize("world", WORLDS)
+@pytest.mark.parametrize("dname", list(TORCH_DT))
+def test_allreduce_matches_reference_fixtures(groups, golden, world, dname):
+    g = groups(world)
+    is_float = dname.startswith("float") or dname == "bfloat16"
+    for oname, op in OPS.items():
+        key = f"allreduce/w{world}/{dname}/{oname}"
+        ins = [_np_view(x, dname) for x in golden[key + "/in"]]
+        ref_apply = _np_view(golden[key + "/apply_op"], dname)
+        ref_gloo = _np_view(golden[key + "/gloo"][0], dname)
+        for aname, algo in _algos(g):
+            if aname == "nvls" and not (oname == "SUM" and dname in ("float32", "float16", "bfloat16")):
+                continue
+            xs = [_to_dev(ins[r], dname, g.device(r)) for r in range(world)]
+            g.run(lambda c, r: c.allreduce(xs[r], op, algo=algo))
+            outs = [_to_np(x, dname) for x in xs]
+            for o in outs[1:]:  # replicas must agree bit for bit (DDP relies on it)
+                assert np.array_equal(o.view(np.uint8), outs[0].view(np.uint8)), (key, aname)
+            got = outs[0]
+            half = dname in ("float16", "bfloat16")
+            if aname == "nvls":
+                if world == 2:
+                    assert np.array_equal(got.view(np.uint8), ref_apply.view(np.uint8)), (key, aname)
+                else:
+                    bound = 1e-6 * np.sum([np.abs(i.astype(np.float64)) for i in ins], axis=0)
+                    if half:
+                        bound = bound + np.abs(ref_apply.astype(np.float64)) * (2.0 ** -8 if dname == "bfloat16" else 2.0 ** -11)
+                    err = np.abs(got.astype(np.float64) - ref_apply.astype(np.float64))
+                    assert np.all(err <= bound), (key, aname, err.max())
+                continue
+            if half and world > 2 and oname in ("SUM", "PRODUCT"):
+                # kernels accumulate 16-bit floats in fp32 and round once
+                want = O.reduce_rank_ascending(ins, op, accumulate="fp32")
+                assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), (key, aname)
+                tol = 2e-2 if dname == "float16" else 1e-1
+                np.testing.assert_allclose(got.astype(np.float64), ref_apply.astype(np.float64), rtol=tol, atol=tol)
+            else:
+                # integers, min/max, fp32/fp64 in rank-ascending order, any single fp add
+                assert np.array_equal(got.view(np.uint8), ref_apply.view(np.uint8)), (key, aname)
+            if dname == "float32" and oname == "SUM":
+                bound = 1e-6 * np.sum([np.abs(i.astype(np.float64)) for i in ins], axis=0)
+                err = np.abs(got.astype(np.float64) - ref_gloo.astype(np.float64))
+                assert np.all(err <= bound), (key, aname, "vs gloo", err.max())
+            if not is_float or oname in ("MIN", "MAX") or world == 2:
+                assert np.array_equal(got.view(np.uint8), ref_gloo.view(np.uint8)), (key, aname, "vs gloo")
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_allreduce_ragged_sizes_and_unaligned_views(groups, world):
+    g = groups(world)
+    from ray_b200 import _native as N
+
+    for numel in (1, 3, 4, 5, 127, 4096, 4097, (1 << 18) + 13):
+        for dtype in (torch.float32, torch.int32, torch.uint8, torch.int64, torch.bfloat16):
+            for algo in (N.ALGO_ONESHOT, N.ALGO_TWOSHOT):
+                gen = torch.Generator().manual_seed(numel)
+                base = [torch.randint(0, 100, (numel + 3,), generator=gen).to(dtype) for _ in range(world)]
+                want = torch.stack([b[3:].to(torch.float64) for b in base]).sum(0)
+                if dtype == torch.uint8:
+                    want = want % 256
+                # view offset by 3 elements: unaligned for 1/2/4-byte types
+                xs = [b.to(g.device(r))[3:] for r, b in enumerate(base)]
+                pads = [x.clone() for x in xs]
+                g.run(lambda c, r: c.allreduce(xs[r], N.SUM, algo=algo))
+                for r in range(world):
+                    assert torch.equal(xs[r].cpu().to(torch.float64), want), (numel, dtype, algo)
+                del pads
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_allreduce_out_of_place_and_empty(groups, world):
+    g = groups(world)
+    xs = [torch.full((1000,), float(r + 1), device=g.device(r)) for r in range(world)]
+    outs = [torch.zeros_like(x) for x in xs]
+    g.run(lambda c, r: c.allreduce(xs[r], 0, out=outs[r]))
+    total = float(sum(range(1, world + 1)))
+    for r in range(world):
+        assert torch.all(outs[r] == total) and torch.all(xs[r] == r + 1)
+    empty = [torch.empty(0, device=g.device(r)) for r in range(world)]
+    g.run(lambda c, r: c.allreduce(empty[r], 0))
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_allreduce_larger_than_staging_is_chunked(groups, world):
+    """Message = 2.5 staging slots: exercises the slot-by-slot loop and the slot rotation."""
+    g = groups(world)
+    numel = (8 << 20) // 4 * 5 // 2 + 7
+    xs = [torch.arange(numel, dtype=torch.int32, device=g.device(r)) * (r + 1) for r in range(world)]
+    g.run(lambda c, r: c.allreduce(xs[r], 0))
+    want = torch.arange(numel, dtype=torch.int64) * sum(range(1, world + 1))
+    for r in range(world):
+        assert torch.equal(xs[r].cpu().to(torch.int64), want)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_allreduce_zero_copy_symmetric_heap(groups, world):
+    g = groups(world)
+    from ray_b200 import _native as N
+
+    numel = 100_003
+    for c in g.comms:
+        c.symm_reset()
+    xs = [g.comms[r].symm_empty((numel,), torch.float32) for r in range(world)]
+    ins = []
+    for r in range(world):
+        v = torch.randn(numel, generator=torch.Generator().manual_seed(r))
+        ins.append(v.numpy())
+        xs[r].copy_(v)
+        assert g.comms[r].symm_contains(xs[r])
+    torch.cuda.synchronize()
+    launches = g.comms[0].launch_count
+    g.run(lambda c, r: c.allreduce(xs[r], N.SUM))
+    assert g.comms[0].launch_count == launches + 1
+    want = O.reduce_rank_ascending(ins, O.SUM)
+    for r in range(world):
+        got = xs[r].cpu().numpy()
+        if g.has_multicast and world > 2:
+            np.testing.assert_allclose(got, want, rtol=0, atol=1e-5)
+        else:
+            assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("world", WORLDS)
+@pytest.mark.parametrize("dname", ["float32", "int32"])
+def test_data_movement_ops_match_reference_fixtures(groups, golden, world, dname):
+    g = groups(world)
+    root = world - 1
+    # broadcast
+    ins = golden[f"broadcast/w{world}/{dname}/in"]
+    xs = [_to_dev(ins[r], dname, g.device(r)) for r in range(world)]
+    g.run(lambda c, r: c.broadcast(xs[r], root))
+    assert np.array_equal(np.stack([_to_np(x, dname) for x in xs]), golden[f"broadcast/w{world}/{dname}/gloo"])
+    # allgather into n separately allocated tensors
+    ins = golden[f"allgather/w{world}/{dname}/in"]
+    xs = [_to_dev(ins[r], dname, g.device(r)) for r in range(world)]
+    outs = [[torch.empty_like(xs[r]) for _ in range(world)] for r in range(world)]
+    g.run(lambda c, r: c.allgather(outs[r], xs[r]))
+    got = np.stack([np.stack([_to_np(o, dname) for o in outs[r]]) for r in range(world)])
+    assert np.array_equal(got, golden[f"allgather/w{world}/{dname}/gloo"])
+    # reduce: only the root changes
+    ins = golden[f"reduce/w{world}/{dname}/in"]
+    xs = [_to_dev(ins[r], dname, g.device(r)) for r in range(world)]
+    g.run(lambda c, r: c.reduce(xs[r], root, 0))
+    want = O.reduce_rank_ascending(list(ins), O.SUM)
+    for r in range(world):
+        assert np.array_equal(_to_np(xs[r], dname), want if r == root else ins[r])
+    gl = golden[f"reduce/w{world}/{dname}/gloo"][root]
+    if dname == "int32" or world == 2:
+        assert np.array_equal(_to_np(xs[root], dname), gl)
+    else:
+        bound = 1e-6 * np.abs(ins.astype(np.float64)).sum(0)
+        assert np.all(np.abs(_to_np(xs[root], dname).astype(np.float64) - gl) <= bound)
+    # send 0 -> world-1
+    ins = golden[f"sendrecv/w{world}/{dname}/in"]
+    xs = [_to_dev(ins[r], dname, g.device(r)) for r in range(world)]
+
+    def p2p(c, r):
+        if r == 0:
+            c.send(xs[0], world - 1)
+        elif r == world - 1:
+            c.recv(xs[r], 0)
+
+    g.run(p2p)
+    assert np.array_equal(np.stack([_to_np(x, dname) for x in xs]), golden[f"sendrecv/w{world}/{dname}/gloo"])
+    # reducescatter straight from the n input tensors
+    ins = golden[f"reducescatter/w{world}/{dname}/in"]  # [rank q][slot i][numel]
+    lists = [[_to_dev(ins[q][i], dname, g.device(q)) for i in range(world)] for q in range(world)]
+    outs = [torch.empty_like(lists[r][0]) for r in range(world)]
+    g.run(lambda c, r: c.reducescatter(outs[r], lists[r], 0))
+    for r in range(world):
+        want = O.reduce_rank_ascending([ins[q][r] for q in range(world)], O.SUM)
+        assert np.array_equal(_to_np(outs[r], dname), want)
+        # inputs are left untouched (NCCL semantics; the gloo emulation overwrites them)
+        for i in range(world):
+            assert np.array_equal(_to_np(lists[r][i], dname), ins[r][i])
+    gl = golden[f"reducescatter/w{world}/{dname}/gloo"]
+    got = np.stack([_to_np(o, dname) for o in outs])
+    if dname == "int32" or world == 2:
+        assert np.array_equal(got, gl)
+    else:
+        np.testing.assert_allclose(got, gl, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_p2p_shapes_sizes_and_back_to_back_messages(groups, world):
+    """Reference p2p tests use shapes up to [5, 9, 10, 85] (test_sendrecv.py:11-37); also
+    messages larger than the inbox ring and several eager sends before the first recv."""
+    g = groups(world)
+    src, dst = 0, world - 1
+    for shape in ([1], [7], [2, 3, 5], [5, 9, 10, 85], [(2 << 20) // 4 * 3 + 5]):
+        a = torch.randn(*shape, device=g.device(src))
+        b = torch.zeros(*shape, device=g.device(dst))
+        g.run(lambda c, r: c.send(a, dst) if r == src else (c.recv(b, src) if r == dst else None))
+        assert torch.equal(a.cpu(), b.cpu()), shape
+    # three small eager messages queued before any receive is posted
+    msgs = [torch.full((100,), float(i), device=g.device(src)) for i in range(3)]
+    outs = [torch.zeros(100, device=g.device(dst)) for _ in range(3)]
+    with torch.cuda.device(g.devices[src]), torch.cuda.stream(g.streams[src]):
+        for m in msgs:
+            g.comms[src].send(m, dst)
+    g.streams[src].synchronize()
+    with torch.cuda.device(g.devices[dst]), torch.cuda.stream(g.streams[dst]):
+        for o in outs:
+            g.comms[dst].recv(o, src)
+    g.synchronize()
+    for i, o in enumerate(outs):
+        assert torch.all(o == i)
+    # ping-pong both directions
+    x = torch.arange(1000, dtype=torch.float16, device=g.device(src))
+    y = torch.zeros(1000, dtype=torch.float16, device=g.device(dst))
+    z = torch.zeros(1000, dtype=torch.float16, device=g.device(src))
+
+    def pingpong(c, r):
+        if r == src:
+            c.send(x, dst)
+            c.recv(z, dst)
+        elif r == dst:
+            c.recv(y, src)
+            c.send(y, src)
+
+    g.run(pingpong)
+    assert torch.equal(z.cpu(), x.cpu())
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_cgraph_layouts_allgather_into_reducescatter_from(groups, world):
+    g = groups(world)
+    d0 = 4 * world
+    xs = [torch.randn(d0, 5, generator=torch.Generator().manual_seed(10 + r)) for r in range(world)]
+    dev = [x.to(g.device(r)) for r, x in enumerate(xs)]
+    cat = [torch.empty(d0 * world, 5, device=g.device(r)) for r in range(world)]
+    g.run(lambda c, r: c.allgather_into(cat[r], dev[r]))
+    want = O.cgraph_allgather([x.numpy() for x in xs])
+    for r in range(world):
+        assert np.array_equal(cat[r].cpu().numpy(), want[r])
+    rs = [torch.empty(d0 // world, 5, device=g.device(r)) for r in range(world)]
+    g.run(lambda c, r: c.reducescatter_from(rs[r], dev[r], 0))
+    want = O.cgraph_reducescatter([x.numpy() for x in xs], 0)
+    for r in range(world):
+        assert np.array_equal(rs[r].cpu().numpy(), want[r])
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("wire", ["f32", "bf16", "f16"])
+def test_fused_gradient_sync_matches_ddp_arithmetic(groups, world, wire):
+    g = groups(world)
+    wdt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[wire]
+    for numel in (1, 1001, (1 << 20) + 3):
+        grads = [torch.randn(numel, generator=torch.Generator().manual_seed(numel + r)) for r in range(world)]
+        dev = [x.to(g.device(r)) for r, x in enumerate(grads)]
+        g.run(lambda c, r: c.grad_allreduce(dev[r], 1.0 / world, wdt))
+        want = O.ddp_grad_sync([x.numpy() for x in grads], wire)[0]
+        outs = [d.cpu().numpy() for d in dev]
+        for o in outs[1:]:
+            assert np.array_equal(o, outs[0])
+        if g.has_multicast and world > 2:
+            tol = {"f32": 1e-6, "bf16": 2.0 ** -8, "f16": 2.0 ** -11}[wire]
+            bound = tol * (np.abs(want) + np.sum([np.abs(x.numpy()) for x in grads], axis=0) / world) + 1e-30
+            assert np.all(np.abs(outs[0] - want) <= bound)
+        else:
+            assert np.array_equal(outs[0], want), (world, wire, numel)
+
+
+def test_fused_gradient_sync_world_size_one(native_lib):
+    from ray_b200.testing import LocalGroup
+
+    with LocalGroup(1) as g:
+        x = torch.randn(1003, device=g.device(0))
+        ref = (x * 0.5).to(torch.bfloat16).float()
+        g.run(lambda c, r: c.grad_allreduce(x, 0.5, torch.bfloat16))
+        assert torch.equal(x, ref)
+        y = torch.arange(10, device=g.device(0), dtype=torch.float32)
+        g.run(lambda c, r: c.allreduce(y, 0))
+        assert torch.equal(y.cpu(), torch.arange(10, dtype=torch.float32))
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_full_size_properties(groups, world):
+    """64 MiB-class messages: properties that do not need an oracle pass over every element.
+    (1) integer all-reduce of a known arithmetic pattern is exact everywhere;
+    (2) all-reduce is linear: AR(a*x) == a*AR(x) for power-of-two a, bit exact;
+    (3) allgather followed by a local sum equals all-reduce for integers."""
+    g = groups(world)
+    numel = (24 << 20) // 4 + 1
+    xs = [(torch.arange(numel, dtype=torch.int32, device=g.device(r)) % 1000) * (r + 1) for r in range(world)]
+    g.run(lambda c, r: c.allreduce(xs[r], 0))
+    want = (torch.arange(numel, dtype=torch.int32, device=g.device(0)) % 1000) * sum(range(1, world + 1))
+    for r in range(world):
+        assert torch.equal(xs[r].to(g.device(0)), want)
+    base = [torch.randn(numel, generator=torch.Generator().manual_seed(r)).to(g.device(r)) for r in range(world)]
+    a = [b.clone() for b in base]
+    b4 = [b * 4.0 for b in base]
+    g.run(lambda c, r: c.allreduce(a[r], 0))
+    g.run(lambda c, r: c.allreduce(b4[r], 0))
+    for r in range(world):
+        assert torch.equal(a[r] * 4.0, b4[r])
+    small = numel // world
+    ints = [torch.randint(-1000, 1000, (small,), dtype=torch.int64, generator=torch.Generator().manual_seed(r)).to(g.device(r))
+            for r in range(world)]
+    outs = [[torch.empty_like(ints[r]) for _ in range(world)] for r in range(world)]
+    g.run(lambda c, r: c.allgather(outs[r], ints[r]))
+    red = [i.clone() for i in ints]
+    g.run(lambda c, r: c.allreduce(red[r], 0))
+    for r in range(world):
+        assert torch.equal(torch.stack(outs[r]).sum(0), red[r])
+
+
+def test_missing_peer_trips_the_watchdog_instead_of_hanging(native_lib):
+    from ray_b200 import _native as N
+    from ray_b200.testing import LocalGroup
+
+    g = LocalGroup(2, timeout_ms=500)
+    try:
+        x = torch.ones(10, device=g.device(0))
+        with torch.cuda.device(g.devices[0]), torch.cuda.stream(g.streams[0]):
+            g.comms[0].allreduce(x, 0)  # rank 1 never joins
+        g.streams[0].synchronize()
+        with pytest.raises(N.B200TimeoutError):
+            g.comms[0].check_status()
+    finally:
+        g.destroy()
+
+
+def test_abort_unblocks_a_pending_receive(native_lib):
+    """Communicator.destroy() must unblock a recv spinning on a peer flag
+    (experimental/channel/nccl_group.py:347-365, SURVEY 'Abort semantics')."""
+    import threading
+    import time
+
+    from ray_b200 import _native as N
+    from ray_b200.testing import LocalGroup
+
+    g = LocalGroup(2, timeout_ms=20000)
+    try:
+        buf = torch.zeros(10, device=g.device(1))
+        with torch.cuda.device(g.devices[1]), torch.cuda.stream(g.streams[1]):
+            g.comms[1].recv(buf, 0)  # nothing will ever be sent
+        t = threading.Timer(0.3, g.comms[1].abort)
+        t0 = time.time()
+        t.start()
+        g.streams[1].synchronize()
+        assert time.time() - t0 < 5.0
+        with pytest.raises(N.B200AbortedError):
+            g.comms[1].check_status()
+        with pytest.raises(N.B200AbortedError):
+            g.comms[1].recv(buf, 0)
+    finally:
+        g.destroy()
