@@ -80,6 +80,8 @@ class LocalGroup:
     def run(self, fn: Callable[[B200Comm, int], None]) -> None:
         """Issue ``fn(comm, rank)`` for every rank on that rank's stream, then wait."""
         for r, c in enumerate(self.comms):
+            # operands are usually produced on the device's default stream: order after it
+            self.streams[r].wait_stream(torch.cuda.current_stream(self.devices[r]))
             with torch.cuda.device(self.devices[r]), torch.cuda.stream(self.streams[r]):
                 fn(c, r)
         self.synchronize()

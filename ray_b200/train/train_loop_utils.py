@@ -56,6 +56,8 @@ def b200_grad_hook(wire_dtype: torch.dtype = torch.bfloat16, process_group: Opti
             return pg.allreduce([buf]).get_future().then(lambda f: f.value()[0])
         return pg.grad_allreduce(buf, 1.0 / pg.size(), wire_dtype)
 
+    # DDP validates the hook's annotations as objects, not strings (distributed.py:_check_comm_hook)
+    hook.__annotations__ = {"bucket": dist.GradBucket, "return": torch.futures.Future[torch.Tensor]}
     return hook
 
 

@@ -33,6 +33,8 @@ class Workers:
 
         def body(r):
             try:
+                # operands are produced on the device's default stream by the test body
+                self.streams[r].wait_stream(torch.cuda.default_stream(self.devices[r]))
                 with torch.cuda.device(self.devices[r]), torch.cuda.stream(self.streams[r]), \
                         self.col.use_manager(self.mgrs[r]):
                     results[r] = fn(r)

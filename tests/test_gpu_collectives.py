@@ -265,6 +265,7 @@ def test_p2p_shapes_sizes_and_back_to_back_messages(groups, world):
     # three small eager messages queued before any receive is posted
     msgs = [torch.full((100,), float(i), device=g.device(src)) for i in range(3)]
     outs = [torch.zeros(100, device=g.device(dst)) for _ in range(3)]
+    torch.cuda.synchronize()
     with torch.cuda.device(g.devices[src]), torch.cuda.stream(g.streams[src]):
         for m in msgs:
             g.comms[src].send(m, dst)
@@ -382,6 +383,7 @@ def test_missing_peer_trips_the_watchdog_instead_of_hanging(native_lib):
     g = LocalGroup(2, timeout_ms=500)
     try:
         x = torch.ones(10, device=g.device(0))
+        torch.cuda.synchronize()
         with torch.cuda.device(g.devices[0]), torch.cuda.stream(g.streams[0]):
             g.comms[0].allreduce(x, 0)  # rank 1 never joins
         g.streams[0].synchronize()
