@@ -29,6 +29,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+def log(msg):
+    """Progress goes to stderr; stdout carries exactly one JSON line."""
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 METRIC = "TorchTrainer ResNet-50 DDP samples/sec"
 UNIT = "samples/s"
 FLOPS_PER_SAMPLE = 24.6e9  # fwd+bwd, 224x224 (SURVEY 8d; 3 x 8.2 GFLOP)
@@ -152,6 +157,7 @@ def run_gpu(args):
     else:
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world, device_id=device)
 
+    log(f"process group up (impl={args.impl}, world={world}); building ResNet-50")
     model = build(device)
     # DDP is applied at world_size 1 too so the gradient-sync path (bucketing + hook) is on the
     # timed path at every N; TorchTrainer itself skips the wrap for a single worker.
@@ -204,9 +210,11 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # CPU tensor -> gloo side of the group
         return float(t.item())
 
+    log("warm-up")
     for _ in range(max(args.warmup, 3)):
         train_step(model, opt, dev_x, dev_y, "cuda")
     torch.cuda.synchronize()
+    log(f"timing {args.steps} steps (inputs resident in HBM)")
 
     launches0 = pg.comm.launch_count if (pg is not None and pg.comm is not None) else 0
     if pg is not None:
@@ -223,6 +231,7 @@ def run_gpu(args):
         for start, end, nbytes in pg.timings:
             kernel_ms.append(start.elapsed_time(end))
             kernel_bytes.append(nbytes)
+    log(f"device-timed: {ms / args.steps:.2f} ms/step; timing end-to-end (host batch in, loss out)")
     # end to end: host batch in, loss out, every step
     for _ in range(2):
         timed(1, resident=False)
@@ -262,6 +271,7 @@ def run_gpu(args):
 
     sweep = None
     if world > 1 and not args.no_sweep:
+        log("all-reduce bandwidth sweep")
         sweep = allreduce_sweep(args, pg, rank, world, device)
 
     line = None
@@ -368,10 +378,10 @@ def cpu_worker(spec_path):
 
 
 def run_cpu_reference(world, steps, warmup, batch):
-    """Runs the CPU path on this host's cores; returns (samples/s, cores, seconds)."""
+    """Runs the CPU path on this host's cores; returns (samples/s, threads used, seconds)."""
     cores = len(os.sched_getaffinity(0))
     with tempfile.TemporaryDirectory(prefix="b200_cpu_ref_") as d:
-        spec = {"world": world, "threads": max(1, cores // world), "batch": batch, "steps": steps,
+        spec = {"world": world, "threads": max(1, min(cores // world, 32)), "batch": batch, "steps": steps,
                 "warmup": warmup, "init": os.path.join(d, "rdzv"), "out": os.path.join(d, "out.json")}
         path = os.path.join(d, "spec.json")
         json.dump(spec, open(path, "w"))
@@ -379,12 +389,18 @@ def run_cpu_reference(world, steps, warmup, batch):
         for r in range(world):
             env = dict(os.environ, RANK=str(r), OMP_NUM_THREADS=str(spec["threads"]), CUDA_VISIBLE_DEVICES="")
             procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", path], env=env))
+        deadline = time.time() + 600
         for p in procs:
-            p.wait()
+            try:
+                p.wait(timeout=max(1.0, deadline - time.time()))
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise RuntimeError("CPU reference worker timed out")
         if any(p.returncode for p in procs):
             raise RuntimeError("CPU reference worker failed")
         secs = json.load(open(spec["out"]))["seconds"]
-    return world * batch * steps / secs, cores, secs
+    return world * batch * steps / secs, world * spec["threads"], secs
 
 
 def run_reference(args):
@@ -411,6 +427,9 @@ def run_reference(args):
 
 
 def main():
+    import faulthandler
+
+    faulthandler.dump_traceback_later(int(os.environ.get("B200_BENCH_WATCHDOG_S", "1500")), exit=True)
     args = parse_args()
     if args.cpu_worker:
         cpu_worker(args.cpu_worker)
@@ -421,6 +440,7 @@ def main():
         line = run_gpu(args)
         if line is not None and line["n_gpus"] == 1 and not args.no_cpu_baseline and args.impl == "b200":
             try:
+                log("cpu_baseline: reference CPU path on the host cores (bounded sample)")
                 v, cores, secs = run_cpu_reference(1, 6, 1, 4)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
                                         "sample": f"6 steps, batch 4, 1 worker, {secs:.1f}s of host time "
