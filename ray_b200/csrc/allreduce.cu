@@ -18,7 +18,7 @@
 // CTA b of every rank works on the same rows in every phase, so a barrier between
 // CTA b's of all ranks (flags in the signal pad) is the only synchronisation needed:
 // no grid-wide sync, no host involvement.
-#include "kernel_utils.cuh"
+#include "allreduce_core.cuh"
 
 namespace b200 {
 
@@ -75,132 +75,66 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_oneshot_kernel(DevComm 
 // ---------------------------------------------------------------------------
 template <typename T, int OP, bool NVLS>
 __global__ void __launch_bounds__(kThreads, 1) allreduce_twoshot_kernel(DevComm c, ARArgs a) {
-  using Tr = Traits<T>;
   const uint32_t launch = c.st->launch_ctr;
   const uint32_t ep = launch * 4u;
-  const int n = c.world, r = c.rank;
-  const int t = threadIdx.x;
   const Units un = make_units(a.nbytes);
-  const size_t U = un.total();
-  const size_t row_units = size_t(n) * kThreads;
-  const size_t R = (U + row_units - 1) / row_units;
+  const RowGeom g = make_rows(un.total(), c.world);
   const bool staged = a.sym_off < 0;
   const size_t off = staged ? staging_slot_offset(launch, a.staging_bytes) : size_t(a.sym_off);
-  const size_t G = gridDim.x;
 
-  // ---- phase 0: stage this CTA's rows into the local symmetric slot -------------
+  // phase 0: stage this CTA's rows into the local symmetric slot
   if (staged) {
     const bool in_al = is_aligned16(a.in);
-    char *mine = c.data[r] + off;
-    for (size_t row = blockIdx.x; row < R; row += G) {
-      uint4 v[kMaxRanks];
-      const size_t base = row * row_units + t;
-#pragma unroll
-      for (int k = 0; k < kMaxRanks; ++k) {
-        const size_t u = base + size_t(k) * kThreads;
-        if (k < n && u < U) v[k] = load_user_unit(a.in, u, un, in_al);
-      }
-#pragma unroll
-      for (int k = 0; k < kMaxRanks; ++k) {
-        const size_t u = base + size_t(k) * kThreads;
-        if (k < n && u < U) st_vec(mine + (u << 4), v[k]);
-      }
-    }
+    stage_in_rows(c, off, g, [&](size_t u) { return load_user_unit(a.in, u, un, in_al); });
   }
-
   if (!cta_barrier_all(c, ep + 1)) {
     finish_launch(c);
     return;
   }
-
-  // ---- phase 1: reduce the units this rank owns, publish to every peer ------------
-  if (NVLS) {
-    constexpr int UNR = 4;
-    char *mc = c.mc_data + off;
-    for (size_t row0 = blockIdx.x; row0 < R; row0 += G * UNR) {
-      uint4 v[UNR];
-#pragma unroll
-      for (int j = 0; j < UNR; ++j) {
-        const size_t row = row0 + size_t(j) * G;
-        const size_t u = row * row_units + size_t(r) * kThreads + t;
-        if (row < R && u < U) v[j] = Multimem<T>::ld_reduce_sum(mc + (u << 4));
-      }
-#pragma unroll
-      for (int j = 0; j < UNR; ++j) {
-        const size_t row = row0 + size_t(j) * G;
-        const size_t u = row * row_units + size_t(r) * kThreads + t;
-        if (row < R && u < U) {
-          if (OP == B200_AVG) {
-            typename Tr::Acc acc = Tr::unpack(v[j]);
-            Tr::average(acc, n);
-            v[j] = Tr::pack(acc);
-          }
-          multimem_st(mc + (u << 4), v[j]);
-        }
-      }
-    }
-  } else {
-    constexpr int UNR = 2;
-    for (size_t row0 = blockIdx.x; row0 < R; row0 += G * UNR) {
-      uint4 v[UNR][kMaxRanks];
-#pragma unroll
-      for (int j = 0; j < UNR; ++j) {
-        const size_t row = row0 + size_t(j) * G;
-        const size_t u = row * row_units + size_t(r) * kThreads + t;
-        if (row < R && u < U) {
-#pragma unroll
-          for (int p = 0; p < kMaxRanks; ++p)
-            if (p < n) v[j][p] = ld_peer(c.data[p] + off + (u << 4));
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < UNR; ++j) {
-        const size_t row = row0 + size_t(j) * G;
-        const size_t u = row * row_units + size_t(r) * kThreads + t;
-        if (row < R && u < U) {
-          typename Tr::Acc acc = Tr::unpack(v[j][0]);
-#pragma unroll
-          for (int p = 1; p < kMaxRanks; ++p)
-            if (p < n) Tr::template reduce<OP>(acc, Tr::unpack(v[j][p]));
-          if (OP == B200_AVG) Tr::average(acc, n);
-          const uint4 res = Tr::pack(acc);
-#pragma unroll
-          for (int i = 0; i < kMaxRanks; ++i) {
-            if (i < n) {
-              int p = r + i;  // start with the local copy, then walk the peers
-              if (p >= n) p -= n;
-              st_vec(c.data[p] + off + (u << 4), res);
-            }
-          }
-        }
-      }
-    }
-  }
-
+  // phase 1: reduce the units this rank owns, publish to every peer
+  reduce_publish_rows<T, OP, NVLS>(c, off, g);
   if (!cta_barrier_all(c, ep + 2)) {
     finish_launch(c);
     return;
   }
-
-  // ---- phase 2: copy this CTA's rows out of the local slot ------------------------
+  // phase 2: copy this CTA's rows out of the local slot
   if (staged) {
     const bool out_al = is_aligned16(a.out);
-    const char *mine = c.data[r] + off;
-    for (size_t row = blockIdx.x; row < R; row += G) {
-      uint4 v[kMaxRanks];
-      const size_t base = row * row_units + t;
-#pragma unroll
-      for (int k = 0; k < kMaxRanks; ++k) {
-        const size_t u = base + size_t(k) * kThreads;
-        if (k < n && u < U) v[k] = ld_peer(mine + (u << 4));
-      }
-#pragma unroll
-      for (int k = 0; k < kMaxRanks; ++k) {
-        const size_t u = base + size_t(k) * kThreads;
-        if (k < n && u < U) store_user_unit(a.out, u, un, out_al, v[k]);
-      }
-    }
+    stage_out_rows(c, off, g, [&](size_t u, uint4 v) { store_user_unit(a.out, u, un, out_al, v); });
   }
+  finish_launch(c);
+}
+
+// ---------------------------------------------------------------------------
+// multi-tensor: the same three phases, but stage-in gathers from / stage-out
+// scatters to a table of tensors, so a list of tensors is reduced as ONE message in ONE
+// launch with no host-side flatten (dag/collective_node.py:220-232 uses parameters_to_vector).
+// ---------------------------------------------------------------------------
+template <typename T, int OP, bool NVLS>
+__global__ void __launch_bounds__(kThreads, 1)
+allreduce_multi_kernel(DevComm c, const __grid_constant__ TensorTable tb, size_t staging_bytes) {
+  const uint32_t launch = c.st->launch_ctr;
+  const uint32_t ep = launch * 4u;
+  const RowGeom g = make_rows(tb.ustart[tb.count], c.world);
+  const size_t off = staging_slot_offset(launch, staging_bytes);
+
+  stage_in_rows(c, off, g, [&](size_t u) {
+    const int i = table_find(tb, u);
+    return load_user_unit(tb.ptr[i], u - tb.ustart[i], make_units(tb.nbytes[i]), is_aligned16(tb.ptr[i]));
+  });
+  if (!cta_barrier_all(c, ep + 1)) {
+    finish_launch(c);
+    return;
+  }
+  reduce_publish_rows<T, OP, NVLS>(c, off, g);
+  if (!cta_barrier_all(c, ep + 2)) {
+    finish_launch(c);
+    return;
+  }
+  stage_out_rows(c, off, g, [&](size_t u, uint4 v) {
+    const int i = table_find(tb, u);
+    store_user_unit(tb.ptr[i], u - tb.ustart[i], make_units(tb.nbytes[i]), is_aligned16(tb.ptr[i]), v);
+  });
   finish_launch(c);
 }
 
@@ -308,6 +242,100 @@ extern "C" int b200_allreduce(b200_comm_t c, const void *in, void *out, size_t c
                         }));
     if (rc) return rc;
     done += nbytes;
+  }
+  return B200_OK;
+}
+
+
+// ---- multi-tensor entry ------------------------------------------------------------
+namespace b200 {
+template <typename T, int OP>
+static int launch_multi(b200_comm *c, const TensorTable &tb, cudaStream_t stream) {
+  const size_t U = tb.ustart[tb.count];
+  const size_t rows = (U + size_t(c->world) * kThreads - 1) / (size_t(c->world) * kThreads);
+  int g = pick_blocks(c, rows, c->sm_count);
+  if constexpr (Multimem<T>::kSum && (OP == B200_SUM || OP == B200_AVG)) {
+    if (c->mc_active) {
+      allreduce_multi_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(c->dev(), tb, c->staging_bytes);
+      B200_LAUNCH_CHECK(c);
+      return B200_OK;
+    }
+  }
+  allreduce_multi_kernel<T, OP, false><<<g, kThreads, 0, stream>>>(c->dev(), tb, c->staging_bytes);
+  B200_LAUNCH_CHECK(c);
+  return B200_OK;
+}
+}  // namespace b200
+
+// Reduces `ntensors` same-dtype tensors as one message: tensors are packed (each starting on
+// a 16-byte unit) into launches of up to kMaxTableTensors tensors / one staging slot.  The
+// single-launch kernel exists for the floating-point types (gradients, activations); other
+// dtypes take one fused launch per tensor.
+extern "C" int b200_allreduce_multi(b200_comm_t c, void *const *ptrs, const size_t *counts,
+                                    int ntensors, int dtype, int op, void *stream_) {
+  int rc = check_usable(c);
+  if (rc) return rc;
+  const size_t es = b200_dtype_size(dtype);
+  if (es == 0) {
+    set_error("unsupported dtype %d", dtype);
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (op < 0 || op >= B200_OP_COUNT) {
+    set_error("unsupported reduce op %d", op);
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (ntensors < 0 || (ntensors > 0 && (!ptrs || !counts))) {
+    set_error("invalid tensor list");
+    return B200_ERR_INVALID;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool table_ok = (dtype == B200_F32 || dtype == B200_F16 || dtype == B200_BF16 || dtype == B200_F64) &&
+                        c->world > 1;
+  int i = 0;
+  while (i < ntensors) {
+    if (counts[i] == 0) {
+      ++i;
+      continue;
+    }
+    if (!ptrs[i]) {
+      set_error("tensor %d is null", i);
+      return B200_ERR_INVALID;
+    }
+    const size_t bytes_i = counts[i] * es;
+    if (!table_ok || bytes_i > c->staging_bytes / 2) {
+      // large tensors (or dtypes without a table kernel) go through the single-tensor path
+      rc = b200_allreduce(c, ptrs[i], ptrs[i], counts[i], dtype, op, B200_ALGO_AUTO, stream_);
+      if (rc) return rc;
+      ++i;
+      continue;
+    }
+    B200_CHECK_CUDA(cudaSetDevice(c->device));
+    TensorTable tb{};
+    size_t units = 0;
+    while (i < ntensors && tb.count < kMaxTableTensors) {
+      if (counts[i] == 0) {
+        ++i;
+        continue;
+      }
+      const size_t b = counts[i] * es;
+      const size_t u = (b + 15) >> 4;
+      if (!ptrs[i] || b > c->staging_bytes / 2 || ((units + u) << 4) > c->staging_bytes) break;
+      tb.ptr[tb.count] = static_cast<char *>(ptrs[i]);
+      tb.nbytes[tb.count] = b;
+      tb.ustart[tb.count] = static_cast<unsigned int>(units);
+      units += u;
+      ++tb.count;
+      ++i;
+    }
+    tb.ustart[tb.count] = static_cast<unsigned int>(units);
+    if (tb.count == 0) continue;
+    switch (dtype) {
+      case B200_F32: B200_DISPATCH_OP(op, OP, { rc = launch_multi<float, OP>(c, tb, stream); }); break;
+      case B200_F64: B200_DISPATCH_OP(op, OP, { rc = launch_multi<double, OP>(c, tb, stream); }); break;
+      case B200_F16: B200_DISPATCH_OP(op, OP, { rc = launch_multi<__half, OP>(c, tb, stream); }); break;
+      default: B200_DISPATCH_OP(op, OP, { rc = launch_multi<__nv_bfloat16, OP>(c, tb, stream); }); break;
+    }
+    if (rc) return rc;
   }
   return B200_OK;
 }

@@ -10,7 +10,7 @@
 //   stage-out: read the reduced wire values, cast back to fp32, write the bucket
 //
 // With wire = bf16 the NVLink traffic and the staging traffic are halved.
-#include "kernel_utils.cuh"
+#include "allreduce_core.cuh"
 
 namespace b200 {
 
@@ -121,114 +121,24 @@ __device__ __forceinline__ void store_grad_unit(float *g, size_t u, size_t count
 
 template <typename W, bool NVLS>
 __global__ void __launch_bounds__(kThreads, 1) grad_allreduce_kernel(DevComm c, GradArgs a) {
-  using Tr = Traits<W>;
   constexpr int E = Wire<W>::kElems;
   const uint32_t launch = c.st->launch_ctr;
   const uint32_t ep = launch * 4u;
-  const int n = c.world, r = c.rank;
-  const int t = threadIdx.x;
-  const size_t U = (a.count + E - 1) / E;
-  const size_t row_units = size_t(n) * kThreads;
-  const size_t R = (U + row_units - 1) / row_units;
+  const RowGeom g = make_rows((a.count + E - 1) / E, c.world);
   const size_t off = staging_slot_offset(launch, a.staging_bytes);
-  const size_t G = gridDim.x;
   const bool al = is_aligned16(a.grad);
-  char *mine = c.data[r] + off;
 
-  for (size_t row = blockIdx.x; row < R; row += G) {
-    uint4 v[kMaxRanks];
-    const size_t base = row * row_units + t;
-#pragma unroll
-    for (int k = 0; k < kMaxRanks; ++k) {
-      const size_t u = base + size_t(k) * kThreads;
-      if (k < n && u < U) v[k] = load_grad_unit<W>(a.grad, u, a.count, a.scale, al);
-    }
-#pragma unroll
-    for (int k = 0; k < kMaxRanks; ++k) {
-      const size_t u = base + size_t(k) * kThreads;
-      if (k < n && u < U) st_vec(mine + (u << 4), v[k]);
-    }
-  }
-
+  stage_in_rows(c, off, g, [&](size_t u) { return load_grad_unit<W>(a.grad, u, a.count, a.scale, al); });
   if (!cta_barrier_all(c, ep + 1)) {
     finish_launch(c);
     return;
   }
-
-  if (NVLS) {
-    constexpr int UNR = 4;
-    char *mc = c.mc_data + off;
-    for (size_t row0 = blockIdx.x; row0 < R; row0 += G * UNR) {
-      uint4 v[UNR];
-#pragma unroll
-      for (int j = 0; j < UNR; ++j) {
-        const size_t row = row0 + size_t(j) * G;
-        const size_t u = row * row_units + size_t(r) * kThreads + t;
-        if (row < R && u < U) v[j] = Multimem<W>::ld_reduce_sum(mc + (u << 4));
-      }
-#pragma unroll
-      for (int j = 0; j < UNR; ++j) {
-        const size_t row = row0 + size_t(j) * G;
-        const size_t u = row * row_units + size_t(r) * kThreads + t;
-        if (row < R && u < U) multimem_st(mc + (u << 4), v[j]);
-      }
-    }
-  } else {
-    constexpr int UNR = 2;
-    for (size_t row0 = blockIdx.x; row0 < R; row0 += G * UNR) {
-      uint4 v[UNR][kMaxRanks];
-#pragma unroll
-      for (int j = 0; j < UNR; ++j) {
-        const size_t row = row0 + size_t(j) * G;
-        const size_t u = row * row_units + size_t(r) * kThreads + t;
-        if (row < R && u < U) {
-#pragma unroll
-          for (int p = 0; p < kMaxRanks; ++p)
-            if (p < n) v[j][p] = ld_peer(c.data[p] + off + (u << 4));
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < UNR; ++j) {
-        const size_t row = row0 + size_t(j) * G;
-        const size_t u = row * row_units + size_t(r) * kThreads + t;
-        if (row < R && u < U) {
-          typename Tr::Acc acc = Tr::unpack(v[j][0]);
-#pragma unroll
-          for (int p = 1; p < kMaxRanks; ++p)
-            if (p < n) Tr::template reduce<B200_SUM>(acc, Tr::unpack(v[j][p]));
-          const uint4 res = Tr::pack(acc);
-#pragma unroll
-          for (int i = 0; i < kMaxRanks; ++i) {
-            if (i < n) {
-              int p = r + i;
-              if (p >= n) p -= n;
-              st_vec(c.data[p] + off + (u << 4), res);
-            }
-          }
-        }
-      }
-    }
-  }
-
+  reduce_publish_rows<W, B200_SUM, NVLS>(c, off, g);
   if (!cta_barrier_all(c, ep + 2)) {
     finish_launch(c);
     return;
   }
-
-  for (size_t row = blockIdx.x; row < R; row += G) {
-    uint4 v[kMaxRanks];
-    const size_t base = row * row_units + t;
-#pragma unroll
-    for (int k = 0; k < kMaxRanks; ++k) {
-      const size_t u = base + size_t(k) * kThreads;
-      if (k < n && u < U) v[k] = ld_peer(mine + (u << 4));
-    }
-#pragma unroll
-    for (int k = 0; k < kMaxRanks; ++k) {
-      const size_t u = base + size_t(k) * kThreads;
-      if (k < n && u < U) store_grad_unit<W>(a.grad, u, a.count, al, v[k]);
-    }
-  }
+  stage_out_rows(c, off, g, [&](size_t u, uint4 v) { store_grad_unit<W>(a.grad, u, a.count, al, v); });
   finish_launch(c);
 }
 
@@ -290,23 +200,6 @@ extern "C" int b200_grad_allreduce(b200_comm_t c, float *grad, size_t count, flo
     else rc = launch_grad<__half>(c, a, stream);
     if (rc) return rc;
     done += n;
-  }
-  return B200_OK;
-}
-
-// Multi-tensor all-reduce: v1 issues one fused launch per tensor (no host-side flatten,
-// no extra device copies); see DESIGN.md for the planned single-launch table variant.
-extern "C" int b200_allreduce_multi(b200_comm_t c, void *const *ptrs, const size_t *counts,
-                                    int ntensors, int dtype, int op, void *stream) {
-  int rc = check_usable(c);
-  if (rc) return rc;
-  if (ntensors < 0 || (ntensors > 0 && (!ptrs || !counts))) {
-    set_error("invalid tensor list");
-    return B200_ERR_INVALID;
-  }
-  for (int i = 0; i < ntensors; ++i) {
-    rc = b200_allreduce(c, ptrs[i], ptrs[i], counts[i], dtype, op, B200_ALGO_AUTO, stream);
-    if (rc) return rc;
   }
   return B200_OK;
 }

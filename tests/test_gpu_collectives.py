@@ -418,3 +418,25 @@ def test_abort_unblocks_a_pending_receive(native_lib):
             g.comms[1].recv(buf, 0)
     finally:
         g.destroy()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_multi_tensor_allreduce_single_launch(groups, world):
+    """SURVEY K9 / dag/collective_node.py:220-232: a list of same-dtype tensors reduced as one
+    message, without a host-side flatten; ragged sizes, one launch for the whole list."""
+    g = groups(world)
+    shapes = [(3,), (17, 5), (1,), (1024,), (33, 33), (7,)]
+    for dtype in (torch.float32, torch.bfloat16, torch.int32):
+        host = [[(torch.randn(s, generator=torch.Generator().manual_seed(7 * r + i)) * 4).round().to(dtype)
+                 for i, s in enumerate(shapes)] for r in range(world)]
+        dev = [[t.to(g.device(r)) for t in host[r]] for r in range(world)]
+        before = g.comms[0].launch_count
+        g.run(lambda c, r: c.allreduce_multi(dev[r], 0))
+        launches = g.comms[0].launch_count - before
+        assert launches == (1 if dtype != torch.int32 else len(shapes)), launches
+        for i in range(len(shapes)):
+            want = torch.stack([host[r][i].to(torch.float64) for r in range(world)]).sum(0)
+            for r in range(world):
+                assert torch.equal(dev[r][i].cpu().to(torch.float64), want), (dtype, i)
+    with pytest.raises(ValueError):
+        g.comms[0].allreduce_multi([torch.ones(2, device=g.device(0)), torch.ones(2, device=g.device(0)).half()])
