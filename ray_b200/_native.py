@@ -29,6 +29,8 @@ ERR_TOO_LARGE = -7
 U8, I8, I32, U32, I64, U64, F16, BF16, F32, F64 = range(10)
 # reduce ops (b200_op_t) -- same numbering as ray.util.collective.types.ReduceOp
 SUM, PROD, MIN, MAX, AVG = range(5)
+# tuning parameters (b200_param_t)
+PARAM_ONESHOT_MAX_BYTES, PARAM_PIPE_MIN_BYTES, PARAM_PIPE_CTAS_IN, PARAM_PIPE_CTAS_OUT = range(4)
 # algorithms (b200_algo_t)
 ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS = range(4)
 
@@ -89,6 +91,7 @@ SIGNATURES = {
     "b200_dtype_size": (c_size_t, [c_int]),
     "b200_comm_launch_count": (c_uint64, [c_void_p]),
     "b200_comm_set_blocks": (c_int, [c_void_p, c_int]),
+    "b200_comm_set_param": (c_int, [c_void_p, c_int, ctypes.c_longlong]),
 }
 
 _lib = None

@@ -135,6 +135,10 @@ class B200Comm:
     def set_blocks(self, nblocks: int) -> None:
         N.check(self._lib.b200_comm_set_blocks(self._h, int(nblocks)))
 
+    def set_param(self, param: int, value: int) -> None:
+        """Tuning knob (``N.PARAM_*``); must be set identically on every rank."""
+        N.check(self._lib.b200_comm_set_param(self._h, int(param), int(value)))
+
     def status(self) -> int:
         return int(self._lib.b200_comm_status(self._h))
 

@@ -18,7 +18,7 @@
 // CTA b of every rank works on the same rows in every phase, so a barrier between
 // CTA b's of all ranks (flags in the signal pad) is the only synchronisation needed:
 // no grid-wide sync, no host involvement.
-#include "allreduce_core.cuh"
+#include "allreduce_pipe.cuh"
 
 namespace b200 {
 
@@ -106,6 +106,22 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_twoshot_kernel(DevComm 
 }
 
 // ---------------------------------------------------------------------------
+// pipelined (role-specialised) staged all-reduce for large messages, see allreduce_pipe.cuh
+// ---------------------------------------------------------------------------
+template <typename T, int OP, bool NVLS>
+__global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, ARArgs a, PipeSplit sp) {
+  const uint32_t launch = c.st->launch_ctr;
+  const Units un = make_units(a.nbytes);
+  const RowGeom g = make_rows(un.total(), c.world);
+  const size_t off = staging_slot_offset(launch, a.staging_bytes);
+  const bool in_al = is_aligned16(a.in), out_al = is_aligned16(a.out);
+  allreduce_pipelined<T, OP, NVLS>(
+      c, launch * 4u + 1u, off, g, sp, [&](size_t u) { return load_user_unit(a.in, u, un, in_al); },
+      [&](size_t u, uint4 v) { store_user_unit(a.out, u, un, out_al, v); });
+  finish_launch(c);
+}
+
+// ---------------------------------------------------------------------------
 // multi-tensor: the same three phases, but stage-in gathers from / stage-out
 // scatters to a table of tensors, so a list of tensors is reduced as ONE message in ONE
 // launch with no host-side flatten (dag/collective_node.py:220-232 uses parameters_to_vector).
@@ -154,13 +170,19 @@ static int launch_allreduce(b200_comm *c, const char *in, char *out, size_t nbyt
   } else {
     const size_t rows = (U + size_t(c->world) * kThreads - 1) / (size_t(c->world) * kThreads);
     int g = pick_blocks(c, rows, c->sm_count);
+    PipeSplit sp{};
+    const bool pipe = sym_off < 0 && nbytes >= pipe_min_bytes(c) && rows <= size_t(kMaxTiles) &&
+                      pick_split(c, g, &sp);
     if (algo == B200_ALGO_NVLS) {
       if constexpr (Multimem<T>::kSum && (OP == B200_SUM || OP == B200_AVG)) {
-        allreduce_twoshot_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(dc, a);
+        if (pipe) allreduce_pipe_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(dc, a, sp);
+        else allreduce_twoshot_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(dc, a);
       } else {
         set_error("NVLS all-reduce supports SUM/AVG on f32/f16/bf16 only");
         return B200_ERR_UNSUPPORTED;
       }
+    } else if (pipe) {
+      allreduce_pipe_kernel<T, OP, false><<<g, kThreads, 0, stream>>>(dc, a, sp);
     } else {
       allreduce_twoshot_kernel<T, OP, false><<<g, kThreads, 0, stream>>>(dc, a);
     }
@@ -174,11 +196,20 @@ static bool nvls_capable(int dtype, int op) {
          (op == B200_SUM || op == B200_AVG);
 }
 
+// Measured on 2/4/8 B200s (profiles/r01): with two ranks the switch reduction saves no
+// traffic and the peer-load kernel is faster; from five ranks on NVLS wins at every size.
+static bool nvls_pays_off(int world, size_t nbytes) {
+  if (world <= 2) return false;
+  if (world <= 4) return nbytes >= (size_t(128) << 20);
+  return true;
+}
+
 static size_t oneshot_limit(const b200_comm *c) {
   static long long env = [] {
     const char *s = getenv("B200_ONESHOT_MAX_BYTES");
     return s ? atoll(s) : -1ll;
   }();
+  if (c->params[B200_PARAM_ONESHOT_MAX_BYTES] >= 0) return size_t(c->params[B200_PARAM_ONESHOT_MAX_BYTES]);
   if (env >= 0) return size_t(env);
   // each rank reads world * nbytes in the one-shot scheme
   return (size_t(1) << 20) / size_t(c->world);
@@ -226,13 +257,13 @@ extern "C" int b200_allreduce(b200_comm_t c, const void *in, void *out, size_t c
   const char *src = static_cast<const char *>(in);
   char *dst = static_cast<char *>(out);
   // Messages larger than one staging slot are processed slot by slot.
-  const size_t chunk_max = sym_off >= 0 ? total : c->staging_bytes;
+  const size_t chunk_max = sym_off >= 0 ? total : c->staging_bytes;  // rows <= kMaxTiles is re-checked per launch
   for (size_t done = 0; done < total;) {
     const size_t nbytes = (total - done) < chunk_max ? (total - done) : chunk_max;
     int a = algo;
     if (a == B200_ALGO_AUTO) {
       if (sym_off < 0 && nbytes <= oneshot_limit(c)) a = B200_ALGO_ONESHOT;
-      else if (c->mc_active && nvls_capable(dtype, op)) a = B200_ALGO_NVLS;
+      else if (c->mc_active && nvls_capable(dtype, op) && nvls_pays_off(c->world, nbytes)) a = B200_ALGO_NVLS;
       else a = B200_ALGO_TWOSHOT;
     }
     if (a == B200_ALGO_ONESHOT && nbytes > c->staging_bytes) a = B200_ALGO_TWOSHOT;

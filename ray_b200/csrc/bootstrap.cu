@@ -835,4 +835,13 @@ int b200_comm_set_blocks(b200_comm_t c, int nblocks) {
   return B200_OK;
 }
 
+int b200_comm_set_param(b200_comm_t c, int param, long long value) {
+  if (!c || param < 0 || param >= B200_PARAM_COUNT) {
+    set_error("unknown parameter %d", param);
+    return B200_ERR_INVALID;
+  }
+  c->params[param] = value;
+  return B200_OK;
+}
+
 }  // extern "C"

@@ -9,6 +9,7 @@
 //                    coll flags  [MAX_BLOCKS][MAX_RANKS]
 //                    p2p ready   [MAX_RANKS src][P2P_RINGS][P2P_SLOTS]
 //                    p2p ack     [MAX_RANKS dst][P2P_RINGS]
+//                    tile-in / tile-out flags [MAX_TILES][MAX_RANKS] (pipelined kernels)
 //   region "inbox" : [MAX_RANKS src] x inbox_bytes point-to-point landing area
 //
 // Rank-local (cudaMalloc) state: launch counter, completion ticket, sticky status,
@@ -33,7 +34,12 @@ constexpr int kP2PSlots = 4;      // chunks in flight per sub-ring
 constexpr size_t kSigCollFlags = 0;
 constexpr size_t kSigP2PReady = kSigCollFlags + size_t(kMaxBlocks) * kMaxRanks;
 constexpr size_t kSigP2PAck = kSigP2PReady + size_t(kMaxRanks) * kP2PRings * kP2PSlots;
-constexpr size_t kSigWords = kSigP2PAck + size_t(kMaxRanks) * kP2PRings;
+// per-tile flags of the pipelined (role-specialised) kernels: "tile staged on rank p" and
+// "rank p published its slice of the tile"
+constexpr int kMaxTiles = 16384;
+constexpr size_t kSigTileIn = kSigP2PAck + size_t(kMaxRanks) * kP2PRings;
+constexpr size_t kSigTileOut = kSigTileIn + size_t(kMaxTiles) * kMaxRanks;
+constexpr size_t kSigWords = kSigTileOut + size_t(kMaxTiles) * kMaxRanks;
 
 // rank-local state words
 struct LocalState {

@@ -440,3 +440,59 @@ def test_multi_tensor_allreduce_single_launch(groups, world):
                 assert torch.equal(dev[r][i].cpu().to(torch.float64), want), (dtype, i)
     with pytest.raises(ValueError):
         g.comms[0].allreduce_multi([torch.ones(2, device=g.device(0)), torch.ones(2, device=g.device(0)).half()])
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_pipelined_role_specialised_kernels_match_oracle(groups, world):
+    """The flag-pipelined large-message kernels (stagers-in / reducers / stagers-out running
+    concurrently) must produce exactly what the phase-by-phase kernels produce."""
+    from ray_b200 import _native as N
+
+    g = groups(world)
+    for c in g.comms:
+        c.set_param(N.PARAM_PIPE_MIN_BYTES, 64 << 10)
+    try:
+        algos = [N.ALGO_TWOSHOT] + ([N.ALGO_NVLS] if g.has_multicast else [])
+        for numel in (16 << 10, (1 << 20) + 77, (3 << 20) + 5):  # last one: chunked over 8 MiB slots
+            ins = [np.random.default_rng(100 * numel + r).standard_normal(numel).astype(np.float32)
+                   for r in range(world)]
+            want = O.reduce_rank_ascending(ins, O.SUM)
+            for algo in algos:
+                xs = [torch.from_numpy(ins[r].copy()).to(g.device(r)) for r in range(world)]
+                before = g.comms[0].launch_count
+                g.run(lambda c, r: c.allreduce(xs[r], N.SUM, algo=algo))
+                assert g.comms[0].launch_count > before
+                for r in range(world):
+                    got = xs[r].cpu().numpy()
+                    if algo == N.ALGO_NVLS and world > 2:
+                        bound = 1e-6 * np.sum([np.abs(i) for i in ins], axis=0)
+                        assert np.all(np.abs(got - want) <= bound)
+                    else:
+                        assert np.array_equal(got, want), (numel, algo)
+            # integers through the peer-load reducers, MAX op, ragged tail
+            ints = [np.random.default_rng(numel + r).integers(-1000, 1000, numel + 3).astype(np.int32)
+                    for r in range(world)]
+            xs = [torch.from_numpy(ints[r].copy()).to(g.device(r)) for r in range(world)]
+            g.run(lambda c, r: c.allreduce(xs[r], N.MAX, algo=N.ALGO_TWOSHOT))
+            for r in range(world):
+                assert np.array_equal(xs[r].cpu().numpy(), O.reduce_rank_ascending(ints, O.MAX))
+        # fused gradient kernel, bf16 wire
+        numel = (2 << 20) + 9
+        grads = [np.random.default_rng(r).standard_normal(numel).astype(np.float32) for r in range(world)]
+        dev = [torch.from_numpy(grads[r].copy()).to(g.device(r)) for r in range(world)]
+        g.run(lambda c, r: c.grad_allreduce(dev[r], 1.0 / world, torch.bfloat16))
+        want = O.ddp_grad_sync(grads, "bf16")[0]
+        for r in range(world):
+            got = dev[r].cpu().numpy()
+            if g.has_multicast and world > 2:
+                assert np.all(np.abs(got - want) <= 2.0 ** -8 * (np.abs(want) + 1e-3))
+            else:
+                assert np.array_equal(got, want)
+        # back-to-back pipelined launches (slot rotation + monotonic tile flags)
+        x = [torch.ones(1 << 20, device=g.device(r)) for r in range(world)]
+        for _ in range(5):
+            g.run(lambda c, r: c.allreduce(x[r], N.SUM, algo=N.ALGO_TWOSHOT))
+        assert torch.all(x[0] == float(world) ** 5)
+    finally:
+        for c in g.comms:
+            c.set_param(N.PARAM_PIPE_MIN_BYTES, -1)
