@@ -106,19 +106,18 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_twoshot_kernel(DevComm 
 }
 
 // ---------------------------------------------------------------------------
-// pipelined (role-specialised) staged all-reduce for large messages, see allreduce_pipe.cuh
+// pipelined (warp-specialised) staged NVLS all-reduce for large messages, see allreduce_pipe.cuh
 // ---------------------------------------------------------------------------
-template <typename T, int OP, bool NVLS>
-__global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, ARArgs a, PipeSplit sp) {
+template <typename T, int OP>
+__global__ void __launch_bounds__(kPipeThreads, 1) allreduce_pipe_kernel(DevComm c, ARArgs a) {
   const uint32_t launch = c.st->launch_ctr;
   const Units un = make_units(a.nbytes);
-  const RowGeom g = make_rows(un.total(), c.world);
   const size_t off = staging_slot_offset(launch, a.staging_bytes);
   const bool in_al = is_aligned16(a.in), out_al = is_aligned16(a.out);
-  allreduce_pipelined<T, OP, NVLS>(
-      c, launch * 4u + 1u, off, g, sp, [&](size_t u) { return load_user_unit(a.in, u, un, in_al); },
+  allreduce_pipelined_nvls<T, OP>(
+      c, launch * 4u + 1u, off, un.total(), [&](size_t u) { return load_user_unit(a.in, u, un, in_al); },
       [&](size_t u, uint4 v) { store_user_unit(a.out, u, un, out_al, v); });
-  finish_launch(c);
+  finish_launch_pipe(c);
 }
 
 // ---------------------------------------------------------------------------
@@ -170,19 +169,16 @@ static int launch_allreduce(b200_comm *c, const char *in, char *out, size_t nbyt
   } else {
     const size_t rows = (U + size_t(c->world) * kThreads - 1) / (size_t(c->world) * kThreads);
     int g = pick_blocks(c, rows, c->sm_count);
-    PipeSplit sp{};
-    const bool pipe = sym_off < 0 && nbytes >= pipe_min_bytes(c) && rows <= size_t(kMaxTiles) &&
-                      pick_split(c, g, &sp);
+    const size_t tiles = pipe_tiles(U, c->world);
+    const bool pipe = sym_off < 0 && nbytes >= pipe_min_bytes(c) && tiles <= size_t(kMaxTiles);
     if (algo == B200_ALGO_NVLS) {
       if constexpr (Multimem<T>::kSum && (OP == B200_SUM || OP == B200_AVG)) {
-        if (pipe) allreduce_pipe_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(dc, a, sp);
+        if (pipe) allreduce_pipe_kernel<T, OP><<<pick_blocks(c, tiles, c->sm_count), kPipeThreads, 0, stream>>>(dc, a);
         else allreduce_twoshot_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(dc, a);
       } else {
         set_error("NVLS all-reduce supports SUM/AVG on f32/f16/bf16 only");
         return B200_ERR_UNSUPPORTED;
       }
-    } else if (pipe) {
-      allreduce_pipe_kernel<T, OP, false><<<g, kThreads, 0, stream>>>(dc, a, sp);
     } else {
       allreduce_twoshot_kernel<T, OP, false><<<g, kThreads, 0, stream>>>(dc, a);
     }
@@ -198,9 +194,11 @@ static bool nvls_capable(int dtype, int op) {
 
 // Measured on 2/4/8 B200s (profiles/r01): with two ranks the switch reduction saves no
 // traffic and the peer-load kernel is faster; from five ranks on NVLS wins at every size.
-static bool nvls_pays_off(int world, size_t nbytes) {
-  if (world <= 2) return false;
-  if (world <= 4) return nbytes >= (size_t(128) << 20);
+static bool nvls_pays_off(const b200_comm *c, size_t nbytes) {
+  const long long min_world = c->params[B200_PARAM_NVLS_MIN_WORLD];
+  if (min_world >= 0) return c->world >= min_world;
+  if (c->world <= 2) return false;
+  if (c->world <= 4) return nbytes >= (size_t(128) << 20);
   return true;
 }
 
@@ -263,7 +261,7 @@ extern "C" int b200_allreduce(b200_comm_t c, const void *in, void *out, size_t c
     int a = algo;
     if (a == B200_ALGO_AUTO) {
       if (sym_off < 0 && nbytes <= oneshot_limit(c)) a = B200_ALGO_ONESHOT;
-      else if (c->mc_active && nvls_capable(dtype, op) && nvls_pays_off(c->world, nbytes)) a = B200_ALGO_NVLS;
+      else if (c->mc_active && nvls_capable(dtype, op) && nvls_pays_off(c, nbytes)) a = B200_ALGO_NVLS;
       else a = B200_ALGO_TWOSHOT;
     }
     if (a == B200_ALGO_ONESHOT && nbytes > c->staging_bytes) a = B200_ALGO_TWOSHOT;

@@ -1,194 +1,175 @@
-// allreduce_pipe.cuh — role-specialised, flag-pipelined all-reduce for large staged messages.
+// allreduce_pipe.cuh — warp-specialised, flag-pipelined NVLS all-reduce for large staged messages.
 //
-// The three phases of the staged all-reduce (stage-in to the symmetric slot, reduce+publish over
-// NVLink / NVSwitch, stage-out to the user tensor) run CONCURRENTLY on disjoint sets of CTAs
-// of one launch instead of back to back separated by grid-wide barriers:
+// The phase-by-phase kernels run stage-in, the NVSwitch reduction and stage-out back to back,
+// separated by cross-GPU barriers: the HBM copies (2 x 2S bytes) sit idle while the NVLink phase
+// runs and vice versa.  Here every CTA has three 256-thread roles that run CONCURRENTLY on the
+// same SM and are coupled only through per-tile flags in the signal pads:
 //
-//   CTAs [0, g_in)              stagers-in : copy tile t of the user tensor into the slot, then
-//                                            release-store flag in[t][me] into every rank's pad
-//   CTAs [g_in, g_in+g_red)     reducers   : wait in[t][p] for all p, reduce the slice this rank
-//                                            owns of tile t (peer loads or multimem.ld_reduce),
-//                                            publish it to every rank (peer stores / multimem.st),
-//                                            release-store flag out[t][me] into every rank's pad
-//   CTAs [g_in+g_red, G)        stagers-out: wait out[t][p] for all p, copy tile t to the user
+//   role 0  stager-in : copy tile t of the user tensor into the symmetric slot, then
+//                       release-store flag in[t][me] into every rank's pad
+//   role 1  reducer   : wait in[t][p] for all p; multimem.ld_reduce the slice of tile t this rank
+//                       owns; multimem.st it to every rank; release-store out[t][me] everywhere
+//   role 2  stager-out: wait out[t][p] for all p; copy tile t from the slot to the user tensor
 //
-// A tile is one row of the row geometry (n*512 16-byte units; rank r owns units [r*512,(r+1)*512)).
-// Flags hold the launch epoch (monotonic), so they are never reset.  HBM staging traffic thus
-// overlaps the NVLink phase; the only serial parts left are the first tile in and the last out.
-//
-// Scheduling order = data-flow order (stagers-in have the lowest CTA indices), so a resident
-// consumer CTA always has its producers resident or finished: no deadlock even if the grid
-// is not fully co-resident.
+// While the reducer warps of an SM wait on NVLink latency, its stager warps keep HBM busy, so
+// the staging traffic hides behind the NVLink phase.  A tile is n*256 16-byte units; rank r
+// owns units [r*256,(r+1)*256) of it.  Flags carry the launch epoch (monotonic): never reset.
+// CTA b's roles all work on tiles b, b+G, ...; the stager-in role never waits, so the data flow
+// cannot deadlock however the CTAs are scheduled.
 #pragma once
 #include "allreduce_core.cuh"
 
 namespace b200 {
 
-struct PipeSplit {
-  int g_in, g_red, g_out;
-};
+constexpr int kPipeRole = 256;             // threads per role
+constexpr int kPipeThreads = 3 * kPipeRole;  // CTA size of the pipelined kernels
 
-// all threads call; threads with `mine` poll `flag` until >= epoch.  Returns false on abort/timeout.
-__device__ __forceinline__ bool cta_wait_flags(const DevComm &c, bool mine, const uint32_t *flag, uint32_t epoch) {
-  int ok = 1;
-  if (mine) ok = wait_flag_ge(c, flag, epoch) ? 1 : 0;
-  return __syncthreads_and(ok) != 0;
+__device__ __forceinline__ void role_bar(int role) {
+  asm volatile("bar.sync %0, %1;" ::"r"(role + 1), "n"(kPipeRole) : "memory");
 }
 
-template <typename T, int OP, bool NVLS, typename LoadFn, typename StoreFn>
-__device__ __forceinline__ void allreduce_pipelined(const DevComm &c, uint32_t epoch, size_t off,
-                                                    const RowGeom &g, PipeSplit sp, LoadFn load, StoreFn store) {
-  using Tr = Traits<T>;
-  const int n = c.world, r = c.rank, t = threadIdx.x, b = blockIdx.x;
-  const size_t T_tiles = g.R;
-  uint32_t *my_in = c.sig[r] + kSigTileIn;
-  uint32_t *my_out = c.sig[r] + kSigTileOut;
+// All threads of `role` call.  Threads with `mine` poll `flag` until >= epoch.  `ok_smem` is the
+// role's shared word.  Returns false if any thread of the role gave up (abort / watchdog).
+__device__ __forceinline__ bool role_wait_flags(const DevComm &c, int role, int *ok_smem, bool mine,
+                                                const uint32_t *flag, uint32_t epoch) {
+  if (mine && !wait_flag_ge(c, flag, epoch)) *ok_smem = 0;
+  role_bar(role);
+  return *ok_smem != 0;
+}
 
-  if (b < sp.g_in) {
-    // ---------------- stager-in: up to 8 loads in flight per thread, tiles signalled one by one
+template <typename T, int OP, typename LoadFn, typename StoreFn>
+__device__ __forceinline__ void allreduce_pipelined_nvls(const DevComm &c, uint32_t epoch, size_t off,
+                                                         size_t U, LoadFn load, StoreFn store) {
+  using Tr = Traits<T>;
+  __shared__ int ok[3];
+  const int n = c.world, r = c.rank;
+  const int role = threadIdx.x / kPipeRole, t = threadIdx.x % kPipeRole;
+  const size_t G = gridDim.x, b = blockIdx.x;
+  const size_t tile_units = size_t(n) * kPipeRole;
+  const size_t T_tiles = (U + tile_units - 1) / tile_units;
+  if (threadIdx.x < 3) ok[threadIdx.x] = 1;
+  __syncthreads();
+
+  if (role == 0) {
+    // ---------------- stager-in: 8 loads in flight per thread
     char *mine = c.data[r] + off;
-    const int tiles_per_iter = n >= 8 ? 1 : 8 / n;
-    for (size_t t0 = size_t(b) * tiles_per_iter; t0 < T_tiles; t0 += size_t(sp.g_in) * tiles_per_iter) {
+    const int tpi = n >= 8 ? 1 : 8 / n;  // tiles per iteration
+    for (size_t k = 0;; ++k) {
+      const size_t first = (k * tpi) * G + b;  // tiles first + j*G
+      if (first >= T_tiles) break;
       uint4 v[8];
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
-        const int j = s / n, k = s - j * n;
-        const size_t u = (t0 + j) * g.row_units + size_t(k) * kThreads + t;
-        if (j < tiles_per_iter && t0 + j < T_tiles && u < g.U) v[s] = load(u);
+        const int j = s / n, q = s - j * n;
+        const size_t tile = first + size_t(j) * G;
+        const size_t u = tile * tile_units + size_t(q) * kPipeRole + t;
+        if (j < tpi && tile < T_tiles && u < U) v[s] = load(u);
       }
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
-        const int j = s / n, k = s - j * n;
-        const size_t u = (t0 + j) * g.row_units + size_t(k) * kThreads + t;
-        if (j < tiles_per_iter && t0 + j < T_tiles && u < g.U) st_vec(mine + (u << 4), v[s]);
+        const int j = s / n, q = s - j * n;
+        const size_t tile = first + size_t(j) * G;
+        const size_t u = tile * tile_units + size_t(q) * kPipeRole + t;
+        if (j < tpi && tile < T_tiles && u < U) st_vec(mine + (u << 4), v[s]);
       }
-      __syncthreads();
-      if (t < n * tiles_per_iter) {
+      role_bar(0);
+      if (t < n * tpi) {
         const int j = t / n, p = t - j * n;
-        if (t0 + j < T_tiles) st_release_sys(c.sig[p] + kSigTileIn + (t0 + j) * kMaxRanks + r, epoch);
+        const size_t tile = first + size_t(j) * G;
+        if (tile < T_tiles) st_release_sys(c.sig[p] + kSigTileIn + tile * kMaxRanks + r, epoch);
       }
     }
-  } else if (b < sp.g_in + sp.g_red) {
-    // ---------------- reducer
-    constexpr int UNR = NVLS ? 4 : 2;
-    const int i = b - sp.g_in;
-    char *mc = NVLS ? c.mc_data + off : nullptr;
-    for (size_t t0 = i; t0 < T_tiles; t0 += size_t(sp.g_red) * UNR) {
-      // wait until every rank staged the tiles of this batch
+  } else if (role == 1) {
+    // ---------------- reducer: 8 multimem.ld_reduce in flight per thread
+    constexpr int UNR = 8;
+    char *mc = c.mc_data + off;
+    const uint32_t *my_in = c.sig[r] + kSigTileIn;
+    for (size_t k = 0;; ++k) {
+      const size_t first = (k * UNR) * G + b;
+      if (first >= T_tiles) break;
       {
         const int j = t / n, p = t - j * n;
-        const size_t tile = t0 + size_t(j) * sp.g_red;
-        const bool mine = t < n * UNR && tile < T_tiles;
-        if (!cta_wait_flags(c, mine, my_in + tile * kMaxRanks + p, epoch)) return;
+        const size_t tile = first + size_t(j) * G;
+        const bool mine_flag = t < n * UNR && tile < T_tiles;
+        if (!role_wait_flags(c, 1, &ok[1], mine_flag, my_in + tile * kMaxRanks + p, epoch)) return;
       }
-      if (NVLS) {
-        uint4 v[UNR];
+      uint4 v[UNR];
 #pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-          const size_t tile = t0 + size_t(j) * sp.g_red;
-          const size_t u = tile * g.row_units + size_t(r) * kThreads + t;
-          if (tile < T_tiles && u < g.U) v[j] = Multimem<T>::ld_reduce_sum(mc + (u << 4));
-        }
+      for (int j = 0; j < UNR; ++j) {
+        const size_t tile = first + size_t(j) * G;
+        const size_t u = tile * tile_units + size_t(r) * kPipeRole + t;
+        if (tile < T_tiles && u < U) v[j] = Multimem<T>::ld_reduce_sum(mc + (u << 4));
+      }
 #pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-          const size_t tile = t0 + size_t(j) * sp.g_red;
-          const size_t u = tile * g.row_units + size_t(r) * kThreads + t;
-          if (tile < T_tiles && u < g.U) {
-            if (OP == B200_AVG) {
-              typename Tr::Acc acc = Tr::unpack(v[j]);
-              Tr::average(acc, n);
-              v[j] = Tr::pack(acc);
-            }
-            multimem_st(mc + (u << 4), v[j]);
+      for (int j = 0; j < UNR; ++j) {
+        const size_t tile = first + size_t(j) * G;
+        const size_t u = tile * tile_units + size_t(r) * kPipeRole + t;
+        if (tile < T_tiles && u < U) {
+          if (OP == B200_AVG) {
+            typename Tr::Acc acc = Tr::unpack(v[j]);
+            Tr::average(acc, n);
+            v[j] = Tr::pack(acc);
           }
-        }
-      } else {
-        uint4 v[UNR][kMaxRanks];
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-          const size_t tile = t0 + size_t(j) * sp.g_red;
-          const size_t u = tile * g.row_units + size_t(r) * kThreads + t;
-          if (tile < T_tiles && u < g.U) {
-#pragma unroll
-            for (int p = 0; p < kMaxRanks; ++p)
-              if (p < n) v[j][p] = ld_peer(c.data[p] + off + (u << 4));
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-          const size_t tile = t0 + size_t(j) * sp.g_red;
-          const size_t u = tile * g.row_units + size_t(r) * kThreads + t;
-          if (tile < T_tiles && u < g.U) {
-            typename Tr::Acc acc = Tr::unpack(v[j][0]);
-#pragma unroll
-            for (int p = 1; p < kMaxRanks; ++p)
-              if (p < n) Tr::template reduce<OP>(acc, Tr::unpack(v[j][p]));
-            if (OP == B200_AVG) Tr::average(acc, n);
-            const uint4 res = Tr::pack(acc);
-#pragma unroll
-            for (int q = 0; q < kMaxRanks; ++q) {
-              if (q < n) {
-                int p = r + q;
-                if (p >= n) p -= n;
-                st_vec(c.data[p] + off + (u << 4), res);
-              }
-            }
-          }
+          multimem_st(mc + (u << 4), v[j]);
         }
       }
-      __syncthreads();
+      role_bar(1);
       if (t < n * UNR) {
         const int j = t / n, p = t - j * n;
-        const size_t tile = t0 + size_t(j) * sp.g_red;
+        const size_t tile = first + size_t(j) * G;
         if (tile < T_tiles) st_release_sys(c.sig[p] + kSigTileOut + tile * kMaxRanks + r, epoch);
       }
     }
   } else {
     // ---------------- stager-out
-    const int i = b - sp.g_in - sp.g_red;
     const char *mine = c.data[r] + off;
-    const int tiles_per_iter = n >= 8 ? 1 : 8 / n;
-    for (size_t t0 = size_t(i) * tiles_per_iter; t0 < T_tiles; t0 += size_t(sp.g_out) * tiles_per_iter) {
+    const uint32_t *my_out = c.sig[r] + kSigTileOut;
+    const int tpi = n >= 8 ? 1 : 8 / n;
+    for (size_t k = 0;; ++k) {
+      const size_t first = (k * tpi) * G + b;
+      if (first >= T_tiles) break;
       {
         const int j = t / n, p = t - j * n;
-        const bool mine_flag = t < n * tiles_per_iter && t0 + j < T_tiles;
-        if (!cta_wait_flags(c, mine_flag, my_out + (t0 + j) * kMaxRanks + p, epoch)) return;
+        const size_t tile = first + size_t(j) * G;
+        const bool mine_flag = t < n * tpi && tile < T_tiles;
+        if (!role_wait_flags(c, 2, &ok[2], mine_flag, my_out + tile * kMaxRanks + p, epoch)) return;
       }
       uint4 v[8];
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
-        const int j = s / n, k = s - j * n;
-        const size_t u = (t0 + j) * g.row_units + size_t(k) * kThreads + t;
-        if (j < tiles_per_iter && t0 + j < T_tiles && u < g.U) v[s] = ld_peer(mine + (u << 4));
+        const int j = s / n, q = s - j * n;
+        const size_t tile = first + size_t(j) * G;
+        const size_t u = tile * tile_units + size_t(q) * kPipeRole + t;
+        if (j < tpi && tile < T_tiles && u < U) v[s] = ld_peer(mine + (u << 4));
       }
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
-        const int j = s / n, k = s - j * n;
-        const size_t u = (t0 + j) * g.row_units + size_t(k) * kThreads + t;
-        if (j < tiles_per_iter && t0 + j < T_tiles && u < g.U) store(u, v[s]);
+        const int j = s / n, q = s - j * n;
+        const size_t tile = first + size_t(j) * G;
+        const size_t u = tile * tile_units + size_t(q) * kPipeRole + t;
+        if (j < tpi && tile < T_tiles && u < U) store(u, v[s]);
       }
     }
   }
 }
 
-// Role split for a grid of G CTAs: explicit B200_PARAM_PIPE_CTAS_IN/OUT, else env
-// B200_PIPE_SPLIT="in,out", else one sixth of the grid on each staging side.
-inline bool pick_split(const b200_comm *c, int G, PipeSplit *sp) {
-  static int env_in = -1, env_out = -1;
-  static bool parsed = false;
-  if (!parsed) {
-    parsed = true;
-    const char *s = getenv("B200_PIPE_SPLIT");
-    if (s) sscanf(s, "%d,%d", &env_in, &env_out);
+// Same completion protocol as finish_launch(), for CTAs whose roles return independently.
+__device__ __forceinline__ void finish_launch_pipe(const DevComm &c) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    uint32_t t = atomicAdd(&c.st->done_ctr, 1u);
+    if (t == gridDim.x - 1) {
+      c.st->done_ctr = 0;
+      __threadfence();
+      atomicAdd(&c.st->launch_ctr, 1u);
+    }
   }
-  int gin = int(c->params[B200_PARAM_PIPE_CTAS_IN]), gout = int(c->params[B200_PARAM_PIPE_CTAS_OUT]);
-  if (gin <= 0) gin = env_in;
-  if (gout <= 0) gout = env_out;
-  if (gin <= 0) gin = G / 6;
-  if (gout <= 0) gout = G / 6;
-  if (gin < 1 || gout < 1 || gin + gout + 1 > G) return false;
-  *sp = PipeSplit{gin, G - gin - gout, gout};
-  return true;
+}
+
+inline size_t pipe_tiles(size_t U, int world) {
+  const size_t tile_units = size_t(world) * kPipeRole;
+  return (U + tile_units - 1) / tile_units;
 }
 
 inline size_t pipe_min_bytes(const b200_comm *c) {

@@ -36,7 +36,7 @@ constexpr size_t kSigP2PReady = kSigCollFlags + size_t(kMaxBlocks) * kMaxRanks;
 constexpr size_t kSigP2PAck = kSigP2PReady + size_t(kMaxRanks) * kP2PRings * kP2PSlots;
 // per-tile flags of the pipelined (role-specialised) kernels: "tile staged on rank p" and
 // "rank p published its slice of the tile"
-constexpr int kMaxTiles = 16384;
+constexpr int kMaxTiles = 32768;
 constexpr size_t kSigTileIn = kSigP2PAck + size_t(kMaxRanks) * kP2PRings;
 constexpr size_t kSigTileOut = kSigTileIn + size_t(kMaxTiles) * kMaxRanks;
 constexpr size_t kSigWords = kSigTileOut + size_t(kMaxTiles) * kMaxRanks;

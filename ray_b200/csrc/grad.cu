@@ -142,18 +142,17 @@ __global__ void __launch_bounds__(kThreads, 1) grad_allreduce_kernel(DevComm c, 
   finish_launch(c);
 }
 
-template <typename W, bool NVLS>
-__global__ void __launch_bounds__(kThreads, 1) grad_pipe_kernel(DevComm c, GradArgs a, PipeSplit sp) {
+template <typename W>
+__global__ void __launch_bounds__(kPipeThreads, 1) grad_pipe_kernel(DevComm c, GradArgs a) {
   constexpr int E = Wire<W>::kElems;
   const uint32_t launch = c.st->launch_ctr;
-  const RowGeom g = make_rows((a.count + E - 1) / E, c.world);
   const size_t off = staging_slot_offset(launch, a.staging_bytes);
   const bool al = is_aligned16(a.grad);
-  allreduce_pipelined<W, B200_SUM, NVLS>(
-      c, launch * 4u + 1u, off, g, sp,
+  allreduce_pipelined_nvls<W, B200_SUM>(
+      c, launch * 4u + 1u, off, (a.count + E - 1) / E,
       [&](size_t u) { return load_grad_unit<W>(a.grad, u, a.count, a.scale, al); },
       [&](size_t u, uint4 v) { store_grad_unit<W>(a.grad, u, a.count, al, v); });
-  finish_launch(c);
+  finish_launch_pipe(c);
 }
 
 // world == 1: the same arithmetic without any peer (scale, round-trip through the wire type).
@@ -178,15 +177,15 @@ static int launch_grad(b200_comm *c, const GradArgs &a, cudaStream_t stream) {
   }
   const size_t rows = (U + size_t(c->world) * kThreads - 1) / (size_t(c->world) * kThreads);
   int g = pick_blocks(c, rows, c->sm_count);
-  PipeSplit sp{};
-  const bool nvls = c->mc_active && c->world > 2;
-  const bool pipe = U * 16 >= pipe_min_bytes(c) && rows <= size_t(kMaxTiles) && pick_split(c, g, &sp);
-  if (pipe) {
-    if (nvls) grad_pipe_kernel<W, true><<<g, kThreads, 0, stream>>>(c->dev(), a, sp);
-    else grad_pipe_kernel<W, false><<<g, kThreads, 0, stream>>>(c->dev(), a, sp);
+  const long long min_world = c->params[B200_PARAM_NVLS_MIN_WORLD] >= 0 ? c->params[B200_PARAM_NVLS_MIN_WORLD] : 3;
+  const bool nvls = c->mc_active && c->world >= min_world;
+  const size_t tiles = pipe_tiles(U, c->world);
+  if (nvls && U * 16 >= pipe_min_bytes(c) && tiles <= size_t(kMaxTiles)) {
+    grad_pipe_kernel<W><<<pick_blocks(c, tiles, c->sm_count), kPipeThreads, 0, stream>>>(c->dev(), a);
+  } else if (nvls) {
+    grad_allreduce_kernel<W, true><<<g, kThreads, 0, stream>>>(c->dev(), a);
   } else {
-    if (nvls) grad_allreduce_kernel<W, true><<<g, kThreads, 0, stream>>>(c->dev(), a);
-    else grad_allreduce_kernel<W, false><<<g, kThreads, 0, stream>>>(c->dev(), a);
+    grad_allreduce_kernel<W, false><<<g, kThreads, 0, stream>>>(c->dev(), a);
   }
   B200_LAUNCH_CHECK(c);
   return B200_OK;

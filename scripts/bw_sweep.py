@@ -67,7 +67,7 @@ def main():
     ap.add_argument("--dtype", default="float32")
     ap.add_argument("--symm", action="store_true", help="operands in the symmetric heap (zero copy)")
     ap.add_argument("--pipe-min", type=int, default=-1, help="B200_PARAM_PIPE_MIN_BYTES (-1 default, huge = off)")
-    ap.add_argument("--splits", default="0:0", help="comma list of in:out CTA counts for the pipelined kernel")
+    ap.add_argument("--nvls-min-world", type=int, default=-1)
     args = ap.parse_args()
     n = args.world
     dtype = getattr(torch, args.dtype)
@@ -77,6 +77,7 @@ def main():
           f"dtype={args.dtype} symm={args.symm}")
     for c in g.comms:
         c.set_param(N.PARAM_PIPE_MIN_BYTES, args.pipe_min)
+        c.set_param(N.PARAM_NVLS_MIN_WORLD, args.nvls_min_world)
     size = args.min
     es = torch.empty((), dtype=dtype).element_size()
     while size <= args.max:
@@ -86,12 +87,8 @@ def main():
             if not g.shared_gpu:
                 for c in g.comms:
                     c.set_blocks(blocks)
-            for aname, split in [(a, sp) for a in args.algos.split(",") for sp in args.splits.split(",")]:
+            for aname in args.algos.split(","):
                 algo = ALGOS[aname]
-                gin, gout = (int(x) for x in split.split(":"))
-                for c in g.comms:
-                    c.set_param(N.PARAM_PIPE_CTAS_IN, gin)
-                    c.set_param(N.PARAM_PIPE_CTAS_OUT, gout)
                 if algo == N.ALGO_NVLS and not g.has_multicast:
                     continue
                 if algo == N.ALGO_ONESHOT and size > (8 << 20):
@@ -129,7 +126,7 @@ def main():
                 torch.cuda.synchronize()
                 us = time_graphs(g, call, iters)
                 algbw = size / us / 1e3
-                print(f"{args.op} {size:>11d} B  algo={aname:8s} blocks={blocks:3d} split={split:7s} {us:10.2f} us  "
+                print(f"{args.op} {size:>11d} B  algo={aname:8s} blocks={blocks:3d} pipe_min={args.pipe_min:<11d} {us:10.2f} us  "
                       f"algbw={algbw:8.1f} GB/s  busbw={algbw * factor:8.1f} GB/s", flush=True)
                 del xs
         size *= args.step

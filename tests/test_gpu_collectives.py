@@ -90,12 +90,14 @@ def test_allreduce_matches_reference_fixtures(groups, golden, world, dname):
             got = outs[0]
             half = dname in ("float16", "bfloat16")
             if aname == "nvls":
-                if world == 2:
+                if world == 2 and not half:
                     assert np.array_equal(got.view(np.uint8), ref_apply.view(np.uint8)), (key, aname)
                 else:
+                    # the switch picks the order, and its 16-bit adder is not bit-identical to an
+                    # IEEE round-to-nearest of the fp32 sum even for two operands
                     bound = 1e-6 * np.sum([np.abs(i.astype(np.float64)) for i in ins], axis=0)
                     if half:
-                        bound = bound + np.abs(ref_apply.astype(np.float64)) * (2.0 ** -8 if dname == "bfloat16" else 2.0 ** -11)
+                        bound = bound + np.abs(ref_apply.astype(np.float64)) * (2.0 ** -7 if dname == "bfloat16" else 2.0 ** -10)
                     err = np.abs(got.astype(np.float64) - ref_apply.astype(np.float64))
                     assert np.all(err <= bound), (key, aname, err.max())
                 continue
@@ -451,6 +453,7 @@ def test_pipelined_role_specialised_kernels_match_oracle(groups, world):
     g = groups(world)
     for c in g.comms:
         c.set_param(N.PARAM_PIPE_MIN_BYTES, 64 << 10)
+        c.set_param(N.PARAM_NVLS_MIN_WORLD, 2)  # exercise the NVLS kernels whenever multicast exists
     try:
         algos = [N.ALGO_TWOSHOT] + ([N.ALGO_NVLS] if g.has_multicast else [])
         for numel in (16 << 10, (1 << 20) + 77, (3 << 20) + 5):  # last one: chunked over 8 MiB slots
@@ -465,7 +468,7 @@ def test_pipelined_role_specialised_kernels_match_oracle(groups, world):
                 for r in range(world):
                     got = xs[r].cpu().numpy()
                     if algo == N.ALGO_NVLS and world > 2:
-                        bound = 1e-6 * np.sum([np.abs(i) for i in ins], axis=0)
+                        bound = 1e-6 * np.sum([np.abs(i) for i in ins], axis=0) + 1e-30
                         assert np.all(np.abs(got - want) <= bound)
                     else:
                         assert np.array_equal(got, want), (numel, algo)
@@ -484,8 +487,8 @@ def test_pipelined_role_specialised_kernels_match_oracle(groups, world):
         want = O.ddp_grad_sync(grads, "bf16")[0]
         for r in range(world):
             got = dev[r].cpu().numpy()
-            if g.has_multicast and world > 2:
-                assert np.all(np.abs(got - want) <= 2.0 ** -8 * (np.abs(want) + 1e-3))
+            if g.has_multicast:
+                assert np.all(np.abs(got - want) <= 2.0 ** -7 * (np.abs(want) + 1e-3))
             else:
                 assert np.array_equal(got, want)
         # back-to-back pipelined launches (slot rotation + monotonic tile flags)
@@ -496,3 +499,4 @@ def test_pipelined_role_specialised_kernels_match_oracle(groups, world):
     finally:
         for c in g.comms:
             c.set_param(N.PARAM_PIPE_MIN_BYTES, -1)
+            c.set_param(N.PARAM_NVLS_MIN_WORLD, -1)
