@@ -203,7 +203,8 @@ typedef enum {
   B200_PARAM_ONESHOT_MAX_BYTES = 0, /* all-reduce messages up to this size use the one-shot kernel */
   B200_PARAM_PIPE_MIN_BYTES = 1,    /* staged messages from this size use the pipelined kernel */
   B200_PARAM_NVLS_MIN_WORLD = 2,    /* AUTO uses the NVLS kernels from this world size on (default 3) */
-  B200_PARAM_COUNT = 3
+  B200_PARAM_NVLS_UNR = 3,          /* multimem.ld_reduce in flight per thread of the phase kernel: 4 (default) or 8 */
+  B200_PARAM_COUNT = 4
 } b200_param_t;
 int b200_comm_set_param(b200_comm_t comm, int param, long long value);
 

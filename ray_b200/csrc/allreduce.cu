@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_oneshot_kernel(DevComm 
 // ---------------------------------------------------------------------------
 // two-shot / NVLS
 // ---------------------------------------------------------------------------
-template <typename T, int OP, bool NVLS>
+template <typename T, int OP, bool NVLS, int NVLS_UNR = 4>
 __global__ void __launch_bounds__(kThreads, 1) allreduce_twoshot_kernel(DevComm c, ARArgs a) {
   const uint32_t launch = c.st->launch_ctr;
   const uint32_t ep = launch * 4u;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_twoshot_kernel(DevComm 
     return;
   }
   // phase 1: reduce the units this rank owns, publish to every peer
-  reduce_publish_rows<T, OP, NVLS>(c, off, g);
+  reduce_publish_rows<T, OP, NVLS, NVLS_UNR>(c, off, g);
   if (!cta_barrier_all(c, ep + 2)) {
     finish_launch(c);
     return;
@@ -174,6 +174,7 @@ static int launch_allreduce(b200_comm *c, const char *in, char *out, size_t nbyt
     if (algo == B200_ALGO_NVLS) {
       if constexpr (Multimem<T>::kSum && (OP == B200_SUM || OP == B200_AVG)) {
         if (pipe) allreduce_pipe_kernel<T, OP><<<pick_blocks(c, tiles, c->sm_count), kPipeThreads, 0, stream>>>(dc, a);
+        else if (c->params[B200_PARAM_NVLS_UNR] == 8) allreduce_twoshot_kernel<T, OP, true, 8><<<g, kThreads, 0, stream>>>(dc, a);
         else allreduce_twoshot_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(dc, a);
       } else {
         set_error("NVLS all-reduce supports SUM/AVG on f32/f16/bf16 only");

@@ -24,13 +24,13 @@ __device__ __forceinline__ RowGeom make_rows(size_t U, int n) {
 
 // Reduce the units this rank owns across all n ranks' buffers at offset `off` of the data
 // region and publish the result into every rank's buffer at the same offset.
-template <typename T, int OP, bool NVLS>
+template <typename T, int OP, bool NVLS, int NVLS_UNR = 4>
 __device__ __forceinline__ void reduce_publish_rows(const DevComm &c, size_t off, const RowGeom &g) {
   using Tr = Traits<T>;
   const int n = c.world, r = c.rank, t = threadIdx.x;
   const size_t G = gridDim.x;
   if (NVLS) {
-    constexpr int UNR = 4;
+    constexpr int UNR = NVLS_UNR;
     char *mc = c.mc_data + off;
     for (size_t row0 = blockIdx.x; row0 < g.R; row0 += G * UNR) {
       uint4 v[UNR];

@@ -51,13 +51,12 @@ __device__ __forceinline__ void allreduce_pipelined_nvls(const DevComm &c, uint3
   __syncthreads();
 
   if (role == 0) {
-    // ---------------- stager-in: 8 loads in flight per thread
+    // ---------------- stager-in: 8 loads in flight per thread.  Software pipelined: the loads of
+    // batch k+1 are issued before the release fence of batch k, so the fence drains behind them.
     char *mine = c.data[r] + off;
-    const int tpi = n >= 8 ? 1 : 8 / n;  // tiles per iteration
-    for (size_t k = 0;; ++k) {
-      const size_t first = (k * tpi) * G + b;  // tiles first + j*G
-      if (first >= T_tiles) break;
-      uint4 v[8];
+    const int tpi = n >= 8 ? 1 : 8 / n;  // tiles per batch
+    uint4 v[8];
+    auto issue_loads = [&](size_t first) {
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
         const int j = s / n, q = s - j * n;
@@ -65,6 +64,10 @@ __device__ __forceinline__ void allreduce_pipelined_nvls(const DevComm &c, uint3
         const size_t u = tile * tile_units + size_t(q) * kPipeRole + t;
         if (j < tpi && tile < T_tiles && u < U) v[s] = load(u);
       }
+    };
+    size_t first = b;
+    if (first < T_tiles) issue_loads(first);
+    while (first < T_tiles) {
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
         const int j = s / n, q = s - j * n;
@@ -72,34 +75,39 @@ __device__ __forceinline__ void allreduce_pipelined_nvls(const DevComm &c, uint3
         const size_t u = tile * tile_units + size_t(q) * kPipeRole + t;
         if (j < tpi && tile < T_tiles && u < U) st_vec(mine + (u << 4), v[s]);
       }
+      const size_t next = first + size_t(tpi) * G;
+      if (next < T_tiles) issue_loads(next);
       role_bar(0);
       if (t < n * tpi) {
         const int j = t / n, p = t - j * n;
         const size_t tile = first + size_t(j) * G;
         if (tile < T_tiles) st_release_sys(c.sig[p] + kSigTileIn + tile * kMaxRanks + r, epoch);
       }
+      first = next;
     }
   } else if (role == 1) {
-    // ---------------- reducer: 8 multimem.ld_reduce in flight per thread
+    // ---------------- reducer: 8 multimem.ld_reduce in flight per thread, software pipelined the
+    // same way (the ld_reduce of batch k+1 are in flight while the multimem.st of batch k drain).
     constexpr int UNR = 8;
     char *mc = c.mc_data + off;
     const uint32_t *my_in = c.sig[r] + kSigTileIn;
-    for (size_t k = 0;; ++k) {
-      const size_t first = (k * UNR) * G + b;
-      if (first >= T_tiles) break;
-      {
-        const int j = t / n, p = t - j * n;
-        const size_t tile = first + size_t(j) * G;
-        const bool mine_flag = t < n * UNR && tile < T_tiles;
-        if (!role_wait_flags(c, 1, &ok[1], mine_flag, my_in + tile * kMaxRanks + p, epoch)) return;
-      }
-      uint4 v[UNR];
+    uint4 v[UNR];
+    auto wait_and_load = [&](size_t first) -> bool {
+      const int j = t / n, p = t - j * n;
+      const size_t ftile = first + size_t(j) * G;
+      const bool mine_flag = t < n * UNR && ftile < T_tiles;
+      if (!role_wait_flags(c, 1, &ok[1], mine_flag, my_in + ftile * kMaxRanks + p, epoch)) return false;
 #pragma unroll
-      for (int j = 0; j < UNR; ++j) {
-        const size_t tile = first + size_t(j) * G;
+      for (int jj = 0; jj < UNR; ++jj) {
+        const size_t tile = first + size_t(jj) * G;
         const size_t u = tile * tile_units + size_t(r) * kPipeRole + t;
-        if (tile < T_tiles && u < U) v[j] = Multimem<T>::ld_reduce_sum(mc + (u << 4));
+        if (tile < T_tiles && u < U) v[jj] = Multimem<T>::ld_reduce_sum(mc + (u << 4));
       }
+      return true;
+    };
+    size_t first = b;
+    if (first < T_tiles && !wait_and_load(first)) return;
+    while (first < T_tiles) {
 #pragma unroll
       for (int j = 0; j < UNR; ++j) {
         const size_t tile = first + size_t(j) * G;
@@ -113,12 +121,18 @@ __device__ __forceinline__ void allreduce_pipelined_nvls(const DevComm &c, uint3
           multimem_st(mc + (u << 4), v[j]);
         }
       }
-      role_bar(1);
+      const size_t next = first + size_t(UNR) * G;
+      if (next < T_tiles) {
+        if (!wait_and_load(next)) return;  // contains the role barrier that orders the stores above
+      } else {
+        role_bar(1);
+      }
       if (t < n * UNR) {
         const int j = t / n, p = t - j * n;
         const size_t tile = first + size_t(j) * G;
         if (tile < T_tiles) st_release_sys(c.sig[p] + kSigTileOut + tile * kMaxRanks + r, epoch);
       }
+      first = next;
     }
   } else {
     // ---------------- stager-out

@@ -68,6 +68,7 @@ def main():
     ap.add_argument("--symm", action="store_true", help="operands in the symmetric heap (zero copy)")
     ap.add_argument("--pipe-min", type=int, default=-1, help="B200_PARAM_PIPE_MIN_BYTES (-1 default, huge = off)")
     ap.add_argument("--nvls-min-world", type=int, default=-1)
+    ap.add_argument("--nvls-unr", type=int, default=-1)
     args = ap.parse_args()
     n = args.world
     dtype = getattr(torch, args.dtype)
@@ -78,6 +79,7 @@ def main():
     for c in g.comms:
         c.set_param(N.PARAM_PIPE_MIN_BYTES, args.pipe_min)
         c.set_param(N.PARAM_NVLS_MIN_WORLD, args.nvls_min_world)
+        c.set_param(N.PARAM_NVLS_UNR, args.nvls_unr)
     size = args.min
     es = torch.empty((), dtype=dtype).element_size()
     while size <= args.max:
