@@ -50,6 +50,8 @@ def parse_args():
                    help="wire dtype of the fused gradient hook; none = plain reducer all-reduce")
     p.add_argument("--no-sweep", action="store_true", help="skip the all-reduce bandwidth sweep (N>1)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--profile", action="store_true",
+                   help="under ncu: skip the end-to-end and sweep legs (numbers printed in this mode are not bench values)")
     p.add_argument("--cpu-worker", default=None, help=argparse.SUPPRESS)
     return p.parse_args()
 
@@ -233,9 +235,12 @@ def run_gpu(args):
             kernel_bytes.append(nbytes)
     log(f"device-timed: {ms / args.steps:.2f} ms/step; timing end-to-end (host batch in, loss out)")
     # end to end: host batch in, loss out, every step
-    for _ in range(2):
-        timed(1, resident=False)
-    ms_e2e = max_over_ranks(timed(args.steps, resident=False))
+    if args.profile:
+        ms_e2e = ms
+    else:
+        for _ in range(2):
+            timed(1, resident=False)
+        ms_e2e = max_over_ranks(timed(args.steps, resident=False))
 
     global_batch = B * world
     value = global_batch * args.steps / (ms / 1e3)
@@ -270,7 +275,7 @@ def run_gpu(args):
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
 
     sweep = None
-    if world > 1 and not args.no_sweep:
+    if world > 1 and not args.no_sweep and not args.profile:
         log("all-reduce bandwidth sweep")
         sweep = allreduce_sweep(args, pg, rank, world, device)
 

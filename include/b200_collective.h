@@ -136,6 +136,15 @@ int b200_symm_reset(b200_comm_t comm);
 /* 1 if [ptr, ptr+nbytes) lies inside this rank's symmetric heap. */
 int b200_symm_contains(b200_comm_t comm, const void *ptr, size_t nbytes);
 
+/* torch.cuda.memory.CUDAPluggableAllocator entry points: after b200_pool_bind(comm) every
+ * allocation torch routes through them comes from comm's symmetric heap, so ordinary
+ * torch tensors created under `torch.cuda.use_mem_pool(...)` are zero-copy operands
+ * (the counterpart of ncclMemAlloc + buffer registration).  All ranks must allocate the
+ * same sequence of sizes.  Blocks are recycled through size-keyed free lists. */
+int b200_pool_bind(b200_comm_t comm);
+void *b200_pool_alloc(size_t size, int device, void *stream);
+void b200_pool_free(void *ptr, size_t size, int device, void *stream);
+
 /* ---- collectives ------------------------------------------------------------ */
 
 /* out[i] = op over ranks of in[i]; in == out allowed (in place).

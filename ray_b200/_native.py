@@ -76,6 +76,9 @@ SIGNATURES = {
     "b200_symm_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "b200_symm_reset": (c_int, [c_void_p]),
     "b200_symm_contains": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "b200_pool_bind": (c_int, [c_void_p]),
+    "b200_pool_alloc": (c_void_p, [c_size_t, c_int, c_void_p]),
+    "b200_pool_free": (None, [c_void_p, c_size_t, c_int, c_void_p]),
     "b200_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "b200_allgather": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_size_t, c_int, c_void_p]),
     "b200_reducescatter": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_size_t, c_int, c_int, c_void_p]),

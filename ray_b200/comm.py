@@ -169,6 +169,20 @@ class B200Comm:
         t._b200_holder = holder  # noqa: SLF001 - keep the mapping alive with the tensor
         return t
 
+    def mem_pool(self):
+        """A ``torch.cuda.MemPool`` whose memory is this communicator's symmetric heap: tensors
+        created under ``with torch.cuda.use_mem_pool(comm.mem_pool()):`` are ordinary torch
+        tensors, yet collectives reduce them in place with no staging copies (what
+        ``ncclMemAlloc`` + buffer registration buys on the NCCL side).  Every rank must create
+        the same tensors in the same order.  One communicator per process can back the pool."""
+        if getattr(self, "_pool", None) is None:
+            from torch.cuda.memory import CUDAPluggableAllocator
+
+            N.check(self._lib.b200_pool_bind(self._h))
+            self._allocator = CUDAPluggableAllocator(str(N.LIB_PATH), "b200_pool_alloc", "b200_pool_free")
+            self._pool = torch.cuda.MemPool(self._allocator.allocator())
+        return self._pool
+
     def symm_reset(self) -> None:
         N.check(self._lib.b200_symm_reset(self._h))
 

@@ -453,6 +453,9 @@ b200::DevComm b200_comm::dev() const {
 }
 
 static std::atomic<uint32_t> g_comm_serial{0};
+static std::mutex g_pool_mu;
+static b200_comm *g_pool_comm = nullptr;
+static std::map<size_t, std::vector<void *>> g_pool_free;  // rounded size -> recycled blocks
 
 extern "C" {
 
@@ -765,6 +768,13 @@ int b200_comm_destroy(b200_comm_t c) {
   if (c->d_state) cudaFree(c->d_state);
   if (c->h_abort) cudaFreeHost(c->h_abort);
   (void)cudaGetLastError();
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool_comm == c) {
+      g_pool_comm = nullptr;
+      g_pool_free.clear();
+    }
+  }
   delete c;
   return B200_OK;
 }
@@ -803,6 +813,48 @@ int b200_symm_contains(b200_comm_t c, const void *ptr, size_t nbytes) {
   const char *base = reinterpret_cast<const char *>(c->data.va[c->rank]) + 2 * c->staging_bytes;
   const char *p = static_cast<const char *>(ptr);
   return p >= base && p + nbytes <= base + c->heap_bytes;
+}
+
+// ---- torch pluggable-allocator bridge ---------------------------------------------------
+
+int b200_pool_bind(b200_comm_t c) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (c) {
+    int rc = check_usable(c);
+    if (rc) return rc;
+    if (c->heap_bytes == 0) {
+      set_error("communicator was created without a symmetric heap (heap_bytes = 0)");
+      return B200_ERR_INVALID;
+    }
+  }
+  g_pool_comm = c;
+  g_pool_free.clear();
+  return B200_OK;
+}
+
+void *b200_pool_alloc(size_t size, int device, void *stream) {
+  (void)stream;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  b200_comm *c = g_pool_comm;
+  if (!c || c->device != device) return nullptr;
+  const size_t need = round_up(size ? size : 1, 512);
+  auto it = g_pool_free.find(need);
+  if (it != g_pool_free.end() && !it->second.empty()) {
+    void *p = it->second.back();
+    it->second.pop_back();
+    return p;
+  }
+  void *out = nullptr;
+  if (b200_symm_alloc(c, need, &out) != B200_OK) return nullptr;
+  return out;
+}
+
+void b200_pool_free(void *ptr, size_t size, int device, void *stream) {
+  (void)device;
+  (void)stream;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (!g_pool_comm || !ptr) return;
+  g_pool_free[round_up(size ? size : 1, 512)].push_back(ptr);
 }
 
 const char *b200_last_error(void) { return g_err; }
