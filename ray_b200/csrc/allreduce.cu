@@ -29,6 +29,7 @@ struct ARArgs {
   size_t staging_bytes;
   long long sym_off;  // >= 0: operand lives in the symmetric data region at this offset
                       //       (zero-copy, in place); < 0: stage through the rotating slot
+  int red_ctas;       // CTAs that run the reduce phase (0 or >= grid: all of them)
 };
 
 // ---------------------------------------------------------------------------
@@ -87,13 +88,8 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_twoshot_kernel(DevComm 
     const bool in_al = is_aligned16(a.in);
     stage_in_rows(c, off, g, [&](size_t u) { return load_user_unit(a.in, u, un, in_al); });
   }
-  if (!cta_barrier_all(c, ep + 1)) {
-    finish_launch(c);
-    return;
-  }
   // phase 1: reduce the units this rank owns, publish to every peer
-  reduce_publish_rows<T, OP, NVLS, NVLS_UNR>(c, off, g);
-  if (!cta_barrier_all(c, ep + 2)) {
+  if (!reduce_phase<T, OP, NVLS, NVLS_UNR>(c, ep, off, g, a.red_ctas)) {
     finish_launch(c);
     return;
   }
@@ -127,7 +123,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) allreduce_pipe_kernel(DevComm
 // ---------------------------------------------------------------------------
 template <typename T, int OP, bool NVLS>
 __global__ void __launch_bounds__(kThreads, 1)
-allreduce_multi_kernel(DevComm c, const __grid_constant__ TensorTable tb, size_t staging_bytes) {
+allreduce_multi_kernel(DevComm c, const __grid_constant__ TensorTable tb, size_t staging_bytes, int red_ctas) {
   const uint32_t launch = c.st->launch_ctr;
   const uint32_t ep = launch * 4u;
   const RowGeom g = make_rows(tb.ustart[tb.count], c.world);
@@ -137,12 +133,7 @@ allreduce_multi_kernel(DevComm c, const __grid_constant__ TensorTable tb, size_t
     const int i = table_find(tb, u);
     return load_user_unit(tb.ptr[i], u - tb.ustart[i], make_units(tb.nbytes[i]), is_aligned16(tb.ptr[i]));
   });
-  if (!cta_barrier_all(c, ep + 1)) {
-    finish_launch(c);
-    return;
-  }
-  reduce_publish_rows<T, OP, NVLS>(c, off, g);
-  if (!cta_barrier_all(c, ep + 2)) {
+  if (!reduce_phase<T, OP, NVLS>(c, ep, off, g, red_ctas)) {
     finish_launch(c);
     return;
   }
@@ -156,11 +147,13 @@ allreduce_multi_kernel(DevComm c, const __grid_constant__ TensorTable tb, size_t
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+static int nvls_ctas(const b200_comm *c);
+
 template <typename T, int OP>
 static int launch_allreduce(b200_comm *c, const char *in, char *out, size_t nbytes, int algo,
                             long long sym_off, cudaStream_t stream) {
   DevComm dc = c->dev();
-  ARArgs a{in, out, nbytes, c->staging_bytes, sym_off};
+  ARArgs a{in, out, nbytes, c->staging_bytes, sym_off, 0};
   const size_t U = make_units(nbytes).total();
   if (algo == B200_ALGO_ONESHOT) {
     a.sym_off = -1;
@@ -170,8 +163,15 @@ static int launch_allreduce(b200_comm *c, const char *in, char *out, size_t nbyt
     const size_t rows = (U + size_t(c->world) * kThreads - 1) / (size_t(c->world) * kThreads);
     int g = pick_blocks(c, rows, c->sm_count);
     const size_t tiles = pipe_tiles(U, c->world);
-    const bool pipe = sym_off < 0 && nbytes >= pipe_min_bytes(c) && tiles <= size_t(kMaxTiles);
+    // explicit opt-in only: measured slower than the phase kernel (profiles/r01/tune_w8_v2_graph.log)
+    const bool pipe = sym_off < 0 && c->params[B200_PARAM_PIPE_MIN_BYTES] >= 0 &&
+                      nbytes >= pipe_min_bytes(c) && tiles <= size_t(kMaxTiles);
     if (algo == B200_ALGO_NVLS) {
+      a.red_ctas = nvls_ctas(c);
+      if (sym_off >= 0) {  // nothing to stage: the whole launch is the reduce phase
+        if (g > a.red_ctas && c->forced_blocks == 0) g = a.red_ctas;
+        a.red_ctas = 0;
+      }
       if constexpr (Multimem<T>::kSum && (OP == B200_SUM || OP == B200_AVG)) {
         if (pipe) allreduce_pipe_kernel<T, OP><<<pick_blocks(c, tiles, c->sm_count), kPipeThreads, 0, stream>>>(dc, a);
         else if (c->params[B200_PARAM_NVLS_UNR] == 8) allreduce_twoshot_kernel<T, OP, true, 8><<<g, kThreads, 0, stream>>>(dc, a);
@@ -201,6 +201,13 @@ static bool nvls_pays_off(const b200_comm *c, size_t nbytes) {
   if (c->world <= 2) return false;
   if (c->world <= 4) return nbytes >= (size_t(128) << 20);
   return true;
+}
+
+// The NVSwitch reduction saturates with far fewer CTAs than the GPU has SMs (measured on
+// 8 B200s, profiles/r01/tune_w8_v2_graph.log: 64 CTAs beat 100 and 148).
+static int nvls_ctas(const b200_comm *c) {
+  const long long v = c->params[B200_PARAM_NVLS_CTAS];
+  return v > 0 ? int(v) : 64;
 }
 
 static size_t oneshot_limit(const b200_comm *c) {
@@ -286,12 +293,12 @@ static int launch_multi(b200_comm *c, const TensorTable &tb, cudaStream_t stream
   int g = pick_blocks(c, rows, c->sm_count);
   if constexpr (Multimem<T>::kSum && (OP == B200_SUM || OP == B200_AVG)) {
     if (c->mc_active) {
-      allreduce_multi_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(c->dev(), tb, c->staging_bytes);
+      allreduce_multi_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(c->dev(), tb, c->staging_bytes, nvls_ctas(c));
       B200_LAUNCH_CHECK(c);
       return B200_OK;
     }
   }
-  allreduce_multi_kernel<T, OP, false><<<g, kThreads, 0, stream>>>(c->dev(), tb, c->staging_bytes);
+  allreduce_multi_kernel<T, OP, false><<<g, kThreads, 0, stream>>>(c->dev(), tb, c->staging_bytes, 0);
   B200_LAUNCH_CHECK(c);
   return B200_OK;
 }

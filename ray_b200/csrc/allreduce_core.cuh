@@ -25,10 +25,11 @@ __device__ __forceinline__ RowGeom make_rows(size_t U, int n) {
 // Reduce the units this rank owns across all n ranks' buffers at offset `off` of the data
 // region and publish the result into every rank's buffer at the same offset.
 template <typename T, int OP, bool NVLS, int NVLS_UNR = 4>
-__device__ __forceinline__ void reduce_publish_rows(const DevComm &c, size_t off, const RowGeom &g) {
+__device__ __forceinline__ void reduce_publish_rows(const DevComm &c, size_t off, const RowGeom &g,
+                                                    size_t G = 0) {
   using Tr = Traits<T>;
   const int n = c.world, r = c.rank, t = threadIdx.x;
-  const size_t G = gridDim.x;
+  if (G == 0) G = gridDim.x;  // CTAs [0, G) share the rows of this phase
   if (NVLS) {
     constexpr int UNR = NVLS_UNR;
     char *mc = c.mc_data + off;
@@ -91,6 +92,28 @@ __device__ __forceinline__ void reduce_publish_rows(const DevComm &c, size_t off
       }
     }
   }
+}
+
+// The synchronised middle of every staged all-reduce: [all ranks staged] -> reduce+publish ->
+// [all ranks published].  With red_ctas in (0, grid) the reduce phase runs on the first
+// red_ctas CTAs only and the two synchronisations become grid-wide flag waits (the row -> CTA
+// mapping differs between the phases); otherwise CTA b only meets CTA b of its peers.
+// Returns false if a wait was abandoned (abort / watchdog).
+template <typename T, int OP, bool NVLS, int NVLS_UNR = 4>
+__device__ __forceinline__ bool reduce_phase(const DevComm &c, uint32_t ep, size_t off, const RowGeom &g,
+                                             int red_ctas) {
+  if (red_ctas > 0 && red_ctas < int(gridDim.x)) {
+    cta_signal_all(c, ep + 1);
+    if (int(blockIdx.x) < red_ctas) {
+      if (!cta_wait_grid(c, gridDim.x, ep + 1)) return false;
+      reduce_publish_rows<T, OP, NVLS, NVLS_UNR>(c, off, g, red_ctas);
+      cta_signal_all(c, ep + 2);
+    }
+    return cta_wait_grid(c, red_ctas, ep + 2);
+  }
+  if (!cta_barrier_all(c, ep + 1)) return false;
+  reduce_publish_rows<T, OP, NVLS, NVLS_UNR>(c, off, g);
+  return cta_barrier_all(c, ep + 2);
 }
 
 // Row-wise staging loops: `load(u)` produces the 16-byte unit u of the (virtual) message,

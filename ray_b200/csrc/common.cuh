@@ -168,6 +168,24 @@ __device__ __forceinline__ bool cta_barrier_all(const DevComm &c, uint32_t epoch
   return ok_flag != 0;
 }
 
+// Grid-wide variant, used when a phase runs on fewer CTAs than the previous one (the NVSwitch
+// reduction saturates at ~64 CTAs while the HBM staging phases want the whole GPU): every CTA
+// announces `epoch`; a CTA that needs ALL of them polls the flags of CTAs [0, nb) of every rank.
+__device__ __forceinline__ void cta_signal_all(const DevComm &c, uint32_t epoch) {
+  __syncthreads();
+  if (threadIdx.x < c.world)
+    st_release_sys(c.sig[threadIdx.x] + kSigCollFlags + size_t(blockIdx.x) * kMaxRanks + c.rank, epoch);
+}
+__device__ __forceinline__ bool cta_wait_grid(const DevComm &c, int nb, uint32_t epoch) {
+  int ok = 1;
+  const uint32_t *flags = c.sig[c.rank] + kSigCollFlags;
+  for (int i = threadIdx.x; i < nb * c.world; i += blockDim.x) {
+    const int b = i / c.world, p = i - b * c.world;
+    if (!wait_flag_ge(c, flags + size_t(b) * kMaxRanks + p, epoch)) ok = 0;
+  }
+  return __syncthreads_and(ok) != 0;
+}
+
 // Called by every CTA at the very end of a collective kernel: the last CTA to get
 // here advances the launch counter (device-resident so the launch sequence can be
 // captured in a CUDA graph).

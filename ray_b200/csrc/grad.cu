@@ -19,6 +19,7 @@ struct GradArgs {
   size_t count;
   float scale;
   size_t staging_bytes;
+  int red_ctas;  // CTAs of the NVLS reduce phase (0 = all)
 };
 
 template <typename W>
@@ -129,12 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1) grad_allreduce_kernel(DevComm c, 
   const bool al = is_aligned16(a.grad);
 
   stage_in_rows(c, off, g, [&](size_t u) { return load_grad_unit<W>(a.grad, u, a.count, a.scale, al); });
-  if (!cta_barrier_all(c, ep + 1)) {
-    finish_launch(c);
-    return;
-  }
-  reduce_publish_rows<W, B200_SUM, NVLS>(c, off, g);
-  if (!cta_barrier_all(c, ep + 2)) {
+  if (!reduce_phase<W, B200_SUM, NVLS>(c, ep, off, g, a.red_ctas)) {
     finish_launch(c);
     return;
   }
@@ -166,7 +162,7 @@ __global__ void grad_local_kernel(GradArgs a) {
 }
 
 template <typename W>
-static int launch_grad(b200_comm *c, const GradArgs &a, cudaStream_t stream) {
+static int launch_grad(b200_comm *c, GradArgs a, cudaStream_t stream) {
   constexpr int E = Wire<W>::kElems;
   const size_t U = (a.count + E - 1) / E;
   if (c->world == 1) {
@@ -180,7 +176,11 @@ static int launch_grad(b200_comm *c, const GradArgs &a, cudaStream_t stream) {
   const long long min_world = c->params[B200_PARAM_NVLS_MIN_WORLD] >= 0 ? c->params[B200_PARAM_NVLS_MIN_WORLD] : 3;
   const bool nvls = c->mc_active && c->world >= min_world;
   const size_t tiles = pipe_tiles(U, c->world);
-  if (nvls && U * 16 >= pipe_min_bytes(c) && tiles <= size_t(kMaxTiles)) {
+  if (!nvls) a.red_ctas = 0;  // peer-load reducers want the whole grid
+  // The warp-specialised pipelined variant measured slower than the phase kernel on 8 GPUs
+  // (profiles/r01/tune_w8_v2_graph.log); it only runs when explicitly enabled.
+  if (nvls && c->params[B200_PARAM_PIPE_MIN_BYTES] >= 0 && U * 16 >= pipe_min_bytes(c) &&
+      tiles <= size_t(kMaxTiles)) {
     grad_pipe_kernel<W><<<pick_blocks(c, tiles, c->sm_count), kPipeThreads, 0, stream>>>(c->dev(), a);
   } else if (nvls) {
     grad_allreduce_kernel<W, true><<<g, kThreads, 0, stream>>>(c->dev(), a);
@@ -215,7 +215,8 @@ extern "C" int b200_grad_allreduce(b200_comm_t c, float *grad, size_t count, flo
   const size_t chunk_elems = (c->staging_bytes / wire_es) & ~size_t(7);
   for (size_t done = 0; done < count;) {
     const size_t n = (count - done) < chunk_elems ? (count - done) : chunk_elems;
-    GradArgs a{grad + done, n, scale, c->staging_bytes};
+    const long long rc_param = c->params[B200_PARAM_NVLS_CTAS];
+    GradArgs a{grad + done, n, scale, c->staging_bytes, rc_param > 0 ? int(rc_param) : 64};
     if (wire_dtype == B200_F32) rc = launch_grad<float>(c, a, stream);
     else if (wire_dtype == B200_BF16) rc = launch_grad<__nv_bfloat16>(c, a, stream);
     else rc = launch_grad<__half>(c, a, stream);

@@ -69,6 +69,7 @@ def main():
     ap.add_argument("--pipe-min", type=int, default=-1, help="B200_PARAM_PIPE_MIN_BYTES (-1 default, huge = off)")
     ap.add_argument("--nvls-min-world", type=int, default=-1)
     ap.add_argument("--nvls-unr", type=int, default=-1)
+    ap.add_argument("--nvls-ctas", default="-1", help="comma list of CTA counts for the NVLS reduce phase")
     args = ap.parse_args()
     n = args.world
     dtype = getattr(torch, args.dtype)
@@ -89,8 +90,10 @@ def main():
             if not g.shared_gpu:
                 for c in g.comms:
                     c.set_blocks(blocks)
-            for aname in args.algos.split(","):
+            for aname, nctas in [(a, int(x)) for a in args.algos.split(",") for x in args.nvls_ctas.split(",")]:
                 algo = ALGOS[aname]
+                for c in g.comms:
+                    c.set_param(N.PARAM_NVLS_CTAS, nctas)
                 if algo == N.ALGO_NVLS and not g.has_multicast:
                     continue
                 if algo == N.ALGO_ONESHOT and size > (8 << 20):
@@ -128,7 +131,7 @@ def main():
                 torch.cuda.synchronize()
                 us = time_graphs(g, call, iters)
                 algbw = size / us / 1e3
-                print(f"{args.op} {size:>11d} B  algo={aname:8s} blocks={blocks:3d} pipe_min={args.pipe_min:<11d} {us:10.2f} us  "
+                print(f"{args.op} {size:>11d} B  algo={aname:8s} blocks={blocks:3d} nvls_ctas={nctas:3d} pipe_min={args.pipe_min:<11d} {us:10.2f} us  "
                       f"algbw={algbw:8.1f} GB/s  busbw={algbw * factor:8.1f} GB/s", flush=True)
                 del xs
         size *= args.step
