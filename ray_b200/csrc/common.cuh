@@ -177,11 +177,38 @@ __device__ __forceinline__ void cta_signal_all(const DevComm &c, uint32_t epoch)
     st_release_sys(c.sig[threadIdx.x] + kSigCollFlags + size_t(blockIdx.x) * kMaxRanks + c.rank, epoch);
 }
 __device__ __forceinline__ bool cta_wait_grid(const DevComm &c, int nb, uint32_t epoch) {
+  // One warp polls, politely: CTAs parked here wait for a whole phase of other CTAs, and
+  // hundreds of threads spinning on system-scope loads would steal L2 bandwidth from the very
+  // NVLink traffic they are waiting for.  Relaxed polls with back-off, one acquire fence at the end.
   int ok = 1;
-  const uint32_t *flags = c.sig[c.rank] + kSigCollFlags;
-  for (int i = threadIdx.x; i < nb * c.world; i += blockDim.x) {
-    const int b = i / c.world, p = i - b * c.world;
-    if (!wait_flag_ge(c, flags + size_t(b) * kMaxRanks + p, epoch)) ok = 0;
+  if (threadIdx.x < 32) {
+    const uint32_t *flags = c.sig[c.rank] + kSigCollFlags;
+    unsigned long long t0 = 0;
+    unsigned sleep_ns = 32;
+    for (int i = threadIdx.x; i < nb * c.world && ok; i += 32) {
+      const int b = i / c.world, p = i - b * c.world;
+      const uint32_t *f = flags + size_t(b) * kMaxRanks + p;
+      unsigned spins = 0;
+      while (int32_t(ld_relaxed_sys(f) - epoch) < 0) {
+        __nanosleep(sleep_ns);
+        if (sleep_ns < 1024) sleep_ns <<= 1;
+        if ((++spins & 0xff) == 0) {
+          if (*c.abort != 0) {
+            atomicCAS(&c.st->status, 0, int(B200_ERR_ABORTED));
+            ok = 0;
+            break;
+          }
+          const unsigned long long now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > c.timeout_ns) {
+            atomicCAS(&c.st->status, 0, int(B200_ERR_TIMEOUT));
+            ok = 0;
+            break;
+          }
+        }
+      }
+    }
+    __threadfence_system();  // acquire: order the polls before the data reads that follow
   }
   return __syncthreads_and(ok) != 0;
 }

@@ -97,7 +97,7 @@ def test_allreduce_matches_reference_fixtures(groups, golden, world, dname):
                     # IEEE round-to-nearest of the fp32 sum even for two operands
                     bound = 1e-6 * np.sum([np.abs(i.astype(np.float64)) for i in ins], axis=0)
                     if half:
-                        bound = bound + np.abs(ref_apply.astype(np.float64)) * (2.0 ** -7 if dname == "bfloat16" else 2.0 ** -10)
+                        bound = bound + np.abs(ref_apply.astype(np.float64)) * (2.0 ** -6 if dname == "bfloat16" else 2.0 ** -9)
                     err = np.abs(got.astype(np.float64) - ref_apply.astype(np.float64))
                     assert np.all(err <= bound), (key, aname, err.max())
                 continue
