@@ -168,8 +168,9 @@ static int launch_allreduce(b200_comm *c, const char *in, char *out, size_t nbyt
                       nbytes >= pipe_min_bytes(c) && tiles <= size_t(kMaxTiles);
     if (algo == B200_ALGO_NVLS) {
       a.red_ctas = nvls_ctas(c);
-      if (sym_off >= 0) {  // nothing to stage: the whole launch is the reduce phase
-        if (g > a.red_ctas && c->forced_blocks == 0) g = a.red_ctas;
+      if (sym_off >= 0) {  // nothing to stage: the whole launch is the reduce phase, which
+        const int cap = a.red_ctas > 0 ? a.red_ctas : 64;  // saturates the switch with ~64 CTAs
+        if (g > cap && c->forced_blocks == 0) g = cap;
         a.red_ctas = 0;
       }
       if constexpr (Multimem<T>::kSum && (OP == B200_SUM || OP == B200_AVG)) {
@@ -203,11 +204,14 @@ static bool nvls_pays_off(const b200_comm *c, size_t nbytes) {
   return true;
 }
 
-// The NVSwitch reduction saturates with far fewer CTAs than the GPU has SMs (measured on
-// 8 B200s, profiles/r01/tune_w8_v2_graph.log: 64 CTAs beat 100 and 148).
+// Zero-copy operands: the NVSwitch reduction saturates with far fewer CTAs than the GPU has SMs
+// (8 B200s, profiles/r01/tune_w8_v2_graph.log: 64 CTAs beat 100 and 148), so those launches are
+// capped at 64 CTAs.  Staged operands keep CTA-to-CTA barriers over the whole grid by default:
+// running their reduce phase on fewer CTAs (this parameter > 0) needs grid-wide waits, which
+// serialise the phases and measured slower (profiles/r01/sweep_w4_nvls_ctas.log).
 static int nvls_ctas(const b200_comm *c) {
   const long long v = c->params[B200_PARAM_NVLS_CTAS];
-  return v > 0 ? int(v) : 64;
+  return v > 0 ? int(v) : 0;
 }
 
 static size_t oneshot_limit(const b200_comm *c) {

@@ -216,7 +216,7 @@ extern "C" int b200_grad_allreduce(b200_comm_t c, float *grad, size_t count, flo
   for (size_t done = 0; done < count;) {
     const size_t n = (count - done) < chunk_elems ? (count - done) : chunk_elems;
     const long long rc_param = c->params[B200_PARAM_NVLS_CTAS];
-    GradArgs a{grad + done, n, scale, c->staging_bytes, rc_param > 0 ? int(rc_param) : 64};
+    GradArgs a{grad + done, n, scale, c->staging_bytes, rc_param > 0 ? int(rc_param) : 0};
     if (wire_dtype == B200_F32) rc = launch_grad<float>(c, a, stream);
     else if (wire_dtype == B200_BF16) rc = launch_grad<__nv_bfloat16>(c, a, stream);
     else rc = launch_grad<__half>(c, a, stream);
