@@ -214,7 +214,8 @@ typedef enum {
   B200_PARAM_NVLS_MIN_WORLD = 2,    /* AUTO uses the NVLS kernels from this world size on (default 3) */
   B200_PARAM_NVLS_UNR = 3,          /* multimem.ld_reduce in flight per thread of the phase kernel: 4 (default) or 8 */
   B200_PARAM_NVLS_CTAS = 4,         /* CTAs of the NVSwitch reduce phase: zero-copy default 64, staged default all */
-  B200_PARAM_COUNT = 5
+  B200_PARAM_FUSED_MIN_BYTES = 5,   /* staged NVLS messages from this size use the interleaved kernel */
+  B200_PARAM_COUNT = 6
 } b200_param_t;
 int b200_comm_set_param(b200_comm_t comm, int param, long long value);
 

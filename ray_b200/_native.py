@@ -30,7 +30,8 @@ U8, I8, I32, U32, I64, U64, F16, BF16, F32, F64 = range(10)
 # reduce ops (b200_op_t) -- same numbering as ray.util.collective.types.ReduceOp
 SUM, PROD, MIN, MAX, AVG = range(5)
 # tuning parameters (b200_param_t)
-PARAM_ONESHOT_MAX_BYTES, PARAM_PIPE_MIN_BYTES, PARAM_NVLS_MIN_WORLD, PARAM_NVLS_UNR, PARAM_NVLS_CTAS = range(5)
+(PARAM_ONESHOT_MAX_BYTES, PARAM_PIPE_MIN_BYTES, PARAM_NVLS_MIN_WORLD, PARAM_NVLS_UNR, PARAM_NVLS_CTAS,
+ PARAM_FUSED_MIN_BYTES) = range(6)
 # algorithms (b200_algo_t)
 ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS = range(4)
 

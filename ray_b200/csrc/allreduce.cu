@@ -18,6 +18,7 @@
 // CTA b of every rank works on the same rows in every phase, so a barrier between
 // CTA b's of all ranks (flags in the signal pad) is the only synchronisation needed:
 // no grid-wide sync, no host involvement.
+#include "allreduce_fused.cuh"
 #include "allreduce_pipe.cuh"
 
 namespace b200 {
@@ -102,6 +103,22 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_twoshot_kernel(DevComm 
 }
 
 // ---------------------------------------------------------------------------
+// fused (interleaved) staged NVLS all-reduce, see allreduce_fused.cuh
+// ---------------------------------------------------------------------------
+template <typename T, int OP>
+__global__ void __launch_bounds__(kThreads, 1) allreduce_fused_kernel(DevComm c, ARArgs a) {
+  const uint32_t launch = c.st->launch_ctr;
+  const Units un = make_units(a.nbytes);
+  const RowGeom g = make_rows(un.total(), c.world);
+  const size_t off = staging_slot_offset(launch, a.staging_bytes);
+  const bool in_al = is_aligned16(a.in), out_al = is_aligned16(a.out);
+  allreduce_fused_nvls<T, OP>(
+      c, off, g, [&](size_t u) { return load_user_unit(a.in, u, un, in_al); },
+      [&](size_t u, uint4 v) { store_user_unit(a.out, u, un, out_al, v); });
+  finish_launch(c);
+}
+
+// ---------------------------------------------------------------------------
 // pipelined (warp-specialised) staged NVLS all-reduce for large messages, see allreduce_pipe.cuh
 // ---------------------------------------------------------------------------
 template <typename T, int OP>
@@ -148,6 +165,10 @@ allreduce_multi_kernel(DevComm c, const __grid_constant__ TensorTable tb, size_t
 // host side
 // ---------------------------------------------------------------------------
 static int nvls_ctas(const b200_comm *c);
+static size_t fused_min_bytes(const b200_comm *c) {
+  const long long v = c->params[B200_PARAM_FUSED_MIN_BYTES];
+  return v >= 0 ? size_t(v) : (size_t(4) << 20);
+}
 
 template <typename T, int OP>
 static int launch_allreduce(b200_comm *c, const char *in, char *out, size_t nbytes, int algo,
@@ -174,7 +195,9 @@ static int launch_allreduce(b200_comm *c, const char *in, char *out, size_t nbyt
         a.red_ctas = 0;
       }
       if constexpr (Multimem<T>::kSum && (OP == B200_SUM || OP == B200_AVG)) {
+        const bool fused = sym_off < 0 && a.red_ctas == 0 && nbytes >= fused_min_bytes(c);
         if (pipe) allreduce_pipe_kernel<T, OP><<<pick_blocks(c, tiles, c->sm_count), kPipeThreads, 0, stream>>>(dc, a);
+        else if (fused) allreduce_fused_kernel<T, OP><<<g, kThreads, 0, stream>>>(dc, a);
         else if (c->params[B200_PARAM_NVLS_UNR] == 8) allreduce_twoshot_kernel<T, OP, true, 8><<<g, kThreads, 0, stream>>>(dc, a);
         else allreduce_twoshot_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(dc, a);
       } else {

@@ -39,7 +39,10 @@ constexpr size_t kSigP2PAck = kSigP2PReady + size_t(kMaxRanks) * kP2PRings * kP2
 constexpr int kMaxTiles = 32768;
 constexpr size_t kSigTileIn = kSigP2PAck + size_t(kMaxRanks) * kP2PRings;
 constexpr size_t kSigTileOut = kSigTileIn + size_t(kMaxTiles) * kMaxRanks;
-constexpr size_t kSigWords = kSigTileOut + size_t(kMaxTiles) * kMaxRanks;
+// row counters of the fused (interleaved) kernels: "rows staged" / "rows published" by CTA b of rank p
+constexpr size_t kSigRowsIn = kSigTileOut + size_t(kMaxTiles) * kMaxRanks;
+constexpr size_t kSigRowsOut = kSigRowsIn + size_t(kMaxBlocks) * kMaxRanks;
+constexpr size_t kSigWords = kSigRowsOut + size_t(kMaxBlocks) * kMaxRanks;
 
 // rank-local state words
 struct LocalState {
@@ -49,6 +52,7 @@ struct LocalState {
   uint32_t pad;
   uint32_t send_seq[kMaxRanks][kP2PRings];  // next chunk sequence to peer, per ring
   uint32_t recv_seq[kMaxRanks][kP2PRings];  // next chunk sequence from peer, per ring
+  uint32_t fused_rows[kMaxBlocks];          // rows ever processed by CTA b in fused kernels
 };
 
 // Passed by value to every kernel.

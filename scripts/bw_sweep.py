@@ -69,6 +69,7 @@ def main():
     ap.add_argument("--pipe-min", type=int, default=-1, help="B200_PARAM_PIPE_MIN_BYTES (-1 default, huge = off)")
     ap.add_argument("--nvls-min-world", type=int, default=-1)
     ap.add_argument("--nvls-unr", type=int, default=-1)
+    ap.add_argument("--fused-min", type=int, default=-1, help="B200_PARAM_FUSED_MIN_BYTES (huge = off)")
     ap.add_argument("--nvls-ctas", default="-1", help="comma list of CTA counts for the NVLS reduce phase")
     args = ap.parse_args()
     n = args.world
@@ -81,6 +82,7 @@ def main():
         c.set_param(N.PARAM_PIPE_MIN_BYTES, args.pipe_min)
         c.set_param(N.PARAM_NVLS_MIN_WORLD, args.nvls_min_world)
         c.set_param(N.PARAM_NVLS_UNR, args.nvls_unr)
+        c.set_param(N.PARAM_FUSED_MIN_BYTES, args.fused_min)
     size = args.min
     es = torch.empty((), dtype=dtype).element_size()
     while size <= args.max:
@@ -131,7 +133,7 @@ def main():
                 torch.cuda.synchronize()
                 us = time_graphs(g, call, iters)
                 algbw = size / us / 1e3
-                print(f"{args.op} {size:>11d} B  algo={aname:8s} blocks={blocks:3d} nvls_ctas={nctas:3d} pipe_min={args.pipe_min:<11d} {us:10.2f} us  "
+                print(f"{args.op} {size:>11d} B  algo={aname:8s} blocks={blocks:3d} nvls_ctas={nctas:3d} pipe_min={args.pipe_min:<3d} fused_min={args.fused_min:<11d} {us:10.2f} us  "
                       f"algbw={algbw:8.1f} GB/s  busbw={algbw * factor:8.1f} GB/s", flush=True)
                 del xs
         size *= args.step

@@ -501,3 +501,60 @@ def test_pipelined_role_specialised_kernels_match_oracle(groups, world):
         for c in g.comms:
             c.set_param(N.PARAM_PIPE_MIN_BYTES, -1)
             c.set_param(N.PARAM_NVLS_MIN_WORLD, -1)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_fused_interleaved_nvls_kernels_match_oracle(groups, world):
+    """The interleaved staged NVLS kernels (allreduce_fused.cuh): multi-row pipelines per CTA,
+    ragged tails, chunking across staging slots, back-to-back launches, fused gradient variant.
+    Needs the multicast mapping, i.e. one GPU per rank."""
+    from ray_b200 import _native as N
+
+    g = groups(world)
+    if not g.has_multicast:
+        pytest.skip("NVLS needs one GPU per rank")
+    for c in g.comms:
+        c.set_param(N.PARAM_FUSED_MIN_BYTES, 0)
+        c.set_param(N.PARAM_NVLS_MIN_WORLD, 2)
+        c.set_blocks(5)  # few CTAs -> many rows per CTA even for small tensors
+    try:
+        for numel in (1, 2049, (1 << 18) + 3, (3 << 20) + 5):
+            ins = [np.random.default_rng(numel + r).standard_normal(numel).astype(np.float32) for r in range(world)]
+            want = O.reduce_rank_ascending(ins, O.SUM)
+            bound = 1e-6 * np.sum([np.abs(i) for i in ins], axis=0) + 1e-30
+            xs = [torch.from_numpy(ins[r].copy()).to(g.device(r)) for r in range(world)]
+            g.run(lambda c, r: c.allreduce(xs[r], N.SUM, algo=N.ALGO_NVLS))
+            outs = [x.cpu().numpy() for x in xs]
+            for o in outs:
+                assert np.array_equal(o, outs[0])
+                if world == 2:
+                    assert np.array_equal(o, want)
+                else:
+                    assert np.all(np.abs(o - want) <= bound)
+            # exact integers carried in fp32 / bf16: every rank, every element
+            ints = [torch.randint(-8, 8, (numel,), generator=torch.Generator().manual_seed(numel + r)).float()
+                    for r in range(world)]
+            for dt in (torch.float32, torch.bfloat16):
+                dev = [i.to(dt).to(g.device(r)) for r, i in enumerate(ints)]
+                for _ in range(3):  # back to back: slot rotation + cumulative row counters
+                    g.run(lambda c, r: c.allreduce(dev[r], N.SUM, algo=N.ALGO_NVLS))
+                    g.run(lambda c, r: dev[r].div_(world))
+                want_i = torch.stack(ints).sum(0) / world
+                for _ in range(2):
+                    want_i = want_i  # mean of identical values stays put after the first round
+                first = torch.stack(ints).sum(0) / world
+                for r in range(world):
+                    assert torch.equal(dev[r].float().cpu(), first.to(dt).float()), (numel, dt)
+            grads = [np.random.default_rng(7 * numel + r).standard_normal(numel).astype(np.float32)
+                     for r in range(world)]
+            dev = [torch.from_numpy(grads[r].copy()).to(g.device(r)) for r in range(world)]
+            g.run(lambda c, r: c.grad_allreduce(dev[r], 1.0 / world, torch.bfloat16))
+            want_g = O.ddp_grad_sync(grads, "bf16")[0]
+            for r in range(world):
+                got = dev[r].cpu().numpy()
+                assert np.all(np.abs(got - want_g) <= 2.0 ** -7 * (np.abs(want_g) + np.sum(np.abs(grads), axis=0) / world))
+    finally:
+        for c in g.comms:
+            c.set_param(N.PARAM_FUSED_MIN_BYTES, -1)
+            c.set_param(N.PARAM_NVLS_MIN_WORLD, -1)
+            c.set_blocks(0)
