@@ -79,7 +79,8 @@ typedef enum {
   B200_ALGO_AUTO = 0,
   B200_ALGO_ONESHOT = 1,  /* every rank reads all peers' staged inputs (latency path) */
   B200_ALGO_TWOSHOT = 2,  /* owner reduces its stripe from peer HBM, pushes result to all peers */
-  B200_ALGO_NVLS = 3      /* multimem.ld_reduce + multimem.st through the NVSwitch */
+  B200_ALGO_NVLS = 3,     /* multimem.ld_reduce + multimem.st through the NVSwitch */
+  B200_ALGO_LL = 4        /* flag-in-data push, no barrier (<= 64 KiB) */
 } b200_algo_t;
 
 typedef struct {
@@ -210,12 +211,10 @@ int b200_comm_set_blocks(b200_comm_t comm, int nblocks);
 /* Tuning parameters (must be set identically on every rank; -1 restores the default). */
 typedef enum {
   B200_PARAM_ONESHOT_MAX_BYTES = 0, /* all-reduce messages up to this size use the one-shot kernel */
-  B200_PARAM_PIPE_MIN_BYTES = 1,    /* staged messages from this size use the pipelined kernel */
-  B200_PARAM_NVLS_MIN_WORLD = 2,    /* AUTO uses the NVLS kernels from this world size on (default 3) */
-  B200_PARAM_NVLS_UNR = 3,          /* multimem.ld_reduce in flight per thread of the phase kernel: 4 (default) or 8 */
-  B200_PARAM_NVLS_CTAS = 4,         /* CTAs of the NVSwitch reduce phase: zero-copy default 64, staged default all */
-  B200_PARAM_FUSED_MIN_BYTES = 5,   /* staged NVLS messages from this size use the interleaved kernel */
-  B200_PARAM_COUNT = 6
+  B200_PARAM_NVLS_MIN_WORLD = 1,    /* AUTO uses the NVLS kernels from this world size on (default 3) */
+  B200_PARAM_NVLS_CTAS = 2,         /* CTAs of the NVSwitch reduce phase: zero-copy default 64, staged default all */
+  B200_PARAM_LL_MAX_BYTES = 3,      /* all-reduce messages up to this size use the LL kernel (default 32 KiB) */
+  B200_PARAM_COUNT = 4
 } b200_param_t;
 int b200_comm_set_param(b200_comm_t comm, int param, long long value);
 

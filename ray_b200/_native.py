@@ -30,10 +30,9 @@ U8, I8, I32, U32, I64, U64, F16, BF16, F32, F64 = range(10)
 # reduce ops (b200_op_t) -- same numbering as ray.util.collective.types.ReduceOp
 SUM, PROD, MIN, MAX, AVG = range(5)
 # tuning parameters (b200_param_t)
-(PARAM_ONESHOT_MAX_BYTES, PARAM_PIPE_MIN_BYTES, PARAM_NVLS_MIN_WORLD, PARAM_NVLS_UNR, PARAM_NVLS_CTAS,
- PARAM_FUSED_MIN_BYTES) = range(6)
+PARAM_ONESHOT_MAX_BYTES, PARAM_NVLS_MIN_WORLD, PARAM_NVLS_CTAS, PARAM_LL_MAX_BYTES = range(4)
 # algorithms (b200_algo_t)
-ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS = range(4)
+ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_LL = range(5)
 
 
 class B200Config(ctypes.Structure):

@@ -23,7 +23,7 @@ BUILD_DIR = CSRC / "build"
 LIB_PATH = PKG_DIR / "libb200_collective.so"
 
 SOURCES = ["bootstrap.cu", "allreduce.cu", "reduce_ops.cu", "copy_ops.cu", "p2p.cu", "grad.cu"]
-HEADERS = ["common.cuh", "comm.h", "kernel_utils.cuh", "allreduce_core.cuh", "allreduce_pipe.cuh", "allreduce_fused.cuh"]
+HEADERS = ["common.cuh", "comm.h", "kernel_utils.cuh", "allreduce_core.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -18,8 +18,7 @@
 // CTA b of every rank works on the same rows in every phase, so a barrier between
 // CTA b's of all ranks (flags in the signal pad) is the only synchronisation needed:
 // no grid-wide sync, no host involvement.
-#include "allreduce_fused.cuh"
-#include "allreduce_pipe.cuh"
+#include "allreduce_core.cuh"
 
 namespace b200 {
 
@@ -73,9 +72,95 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_oneshot_kernel(DevComm 
 }
 
 // ---------------------------------------------------------------------------
+// low-latency (LL) one-shot: every rank pushes its message straight into each peer's LL slot as
+// (word, flag) pairs -- 16-byte stores carrying two pairs, each 8-byte pair lands atomically --
+// and then polls its own slots until the flags of this launch appear.  No barrier, no staging
+// pass: one NVLink traversal end to end.  At most one 16-byte unit per thread.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void ll_store(void *p, uint32_t a, uint32_t b, uint32_t flag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(flag), "r"(b), "r"(flag)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ll_load(const void *p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(kThreads, 1) allreduce_ll_kernel(DevComm c, ARArgs a) {
+  using Tr = Traits<T>;
+  const uint32_t launch = c.st->launch_ctr;
+  const uint32_t flag = launch + 1u;  // never 0, never equal to what the slot held two launches ago
+  const int n = c.world, r = c.rank;
+  const Units un = make_units(a.nbytes);
+  const size_t U = un.total();
+  const size_t u = size_t(blockIdx.x) * kThreads + threadIdx.x;
+  const size_t par_off = (launch & 1u) ? size_t(kMaxRanks) * kLLSlotBytes : 0;
+  if (u < U) {
+    const uint4 mine = load_user_unit(a.in, u, un, is_aligned16(a.in));
+    // push (start with the next rank so the eight peers are not hit in lock step)
+#pragma unroll
+    for (int i = 1; i < kMaxRanks; ++i) {
+      if (i < n) {
+        int p = r + i;
+        if (p >= n) p -= n;
+        char *dst = c.ll[p] + par_off + size_t(r) * kLLSlotBytes + (u << 5);
+        ll_store(dst, mine.x, mine.y, flag);
+        ll_store(dst + 16, mine.z, mine.w, flag);
+      }
+    }
+    // collect, rank-ascending
+    const char *base = c.ll[r] + par_off + (u << 5);
+    typename Tr::Acc acc;
+    bool alive = true;
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) {
+      if (p < n) {
+        uint4 v = mine;
+        if (p != r) {
+          const char *src = base + size_t(p) * kLLSlotBytes;
+          uint4 lo, hi;
+          unsigned spins = 0;
+          unsigned long long t0 = 0;
+          while (alive) {
+            lo = ll_load(src);
+            hi = ll_load(src + 16);
+            if (lo.y == flag && lo.w == flag && hi.y == flag && hi.w == flag) break;
+            if ((++spins & 0x3ff) == 0) {
+              if (*c.abort != 0) {
+                atomicCAS(&c.st->status, 0, int(B200_ERR_ABORTED));
+                alive = false;
+              }
+              const unsigned long long now = globaltimer_ns();
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > c.timeout_ns) {
+                atomicCAS(&c.st->status, 0, int(B200_ERR_TIMEOUT));
+                alive = false;
+              }
+            }
+          }
+          v = make_uint4(lo.x, lo.z, hi.x, hi.z);
+        }
+        if (p == 0) acc = Tr::unpack(v);
+        else Tr::template reduce<OP>(acc, Tr::unpack(v));
+      }
+    }
+    if (alive) {
+      if (OP == B200_AVG) Tr::average(acc, n);
+      store_user_unit(a.out, u, un, is_aligned16(a.out), Tr::pack(acc));
+    }
+  }
+  finish_launch(c);
+}
+
+// ---------------------------------------------------------------------------
 // two-shot / NVLS
 // ---------------------------------------------------------------------------
-template <typename T, int OP, bool NVLS, int NVLS_UNR = 4>
+template <typename T, int OP, bool NVLS>
 __global__ void __launch_bounds__(kThreads, 1) allreduce_twoshot_kernel(DevComm c, ARArgs a) {
   const uint32_t launch = c.st->launch_ctr;
   const uint32_t ep = launch * 4u;
@@ -90,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_twoshot_kernel(DevComm 
     stage_in_rows(c, off, g, [&](size_t u) { return load_user_unit(a.in, u, un, in_al); });
   }
   // phase 1: reduce the units this rank owns, publish to every peer
-  if (!reduce_phase<T, OP, NVLS, NVLS_UNR>(c, ep, off, g, a.red_ctas)) {
+  if (!reduce_phase<T, OP, NVLS>(c, ep, off, g, a.red_ctas)) {
     finish_launch(c);
     return;
   }
@@ -100,37 +185,6 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_twoshot_kernel(DevComm 
     stage_out_rows(c, off, g, [&](size_t u, uint4 v) { store_user_unit(a.out, u, un, out_al, v); });
   }
   finish_launch(c);
-}
-
-// ---------------------------------------------------------------------------
-// fused (interleaved) staged NVLS all-reduce, see allreduce_fused.cuh
-// ---------------------------------------------------------------------------
-template <typename T, int OP>
-__global__ void __launch_bounds__(kThreads, 1) allreduce_fused_kernel(DevComm c, ARArgs a) {
-  const uint32_t launch = c.st->launch_ctr;
-  const Units un = make_units(a.nbytes);
-  const RowGeom g = make_rows(un.total(), c.world);
-  const size_t off = staging_slot_offset(launch, a.staging_bytes);
-  const bool in_al = is_aligned16(a.in), out_al = is_aligned16(a.out);
-  allreduce_fused_nvls<T, OP>(
-      c, off, g, [&](size_t u) { return load_user_unit(a.in, u, un, in_al); },
-      [&](size_t u, uint4 v) { store_user_unit(a.out, u, un, out_al, v); });
-  finish_launch(c);
-}
-
-// ---------------------------------------------------------------------------
-// pipelined (warp-specialised) staged NVLS all-reduce for large messages, see allreduce_pipe.cuh
-// ---------------------------------------------------------------------------
-template <typename T, int OP>
-__global__ void __launch_bounds__(kPipeThreads, 1) allreduce_pipe_kernel(DevComm c, ARArgs a) {
-  const uint32_t launch = c.st->launch_ctr;
-  const Units un = make_units(a.nbytes);
-  const size_t off = staging_slot_offset(launch, a.staging_bytes);
-  const bool in_al = is_aligned16(a.in), out_al = is_aligned16(a.out);
-  allreduce_pipelined_nvls<T, OP>(
-      c, launch * 4u + 1u, off, un.total(), [&](size_t u) { return load_user_unit(a.in, u, un, in_al); },
-      [&](size_t u, uint4 v) { store_user_unit(a.out, u, un, out_al, v); });
-  finish_launch_pipe(c);
 }
 
 // ---------------------------------------------------------------------------
@@ -165,28 +219,23 @@ allreduce_multi_kernel(DevComm c, const __grid_constant__ TensorTable tb, size_t
 // host side
 // ---------------------------------------------------------------------------
 static int nvls_ctas(const b200_comm *c);
-static size_t fused_min_bytes(const b200_comm *c) {
-  const long long v = c->params[B200_PARAM_FUSED_MIN_BYTES];
-  return v >= 0 ? size_t(v) : (size_t(4) << 20);
-}
-
+static size_t ll_limit(const b200_comm *c);
 template <typename T, int OP>
 static int launch_allreduce(b200_comm *c, const char *in, char *out, size_t nbytes, int algo,
                             long long sym_off, cudaStream_t stream) {
   DevComm dc = c->dev();
   ARArgs a{in, out, nbytes, c->staging_bytes, sym_off, 0};
   const size_t U = make_units(nbytes).total();
-  if (algo == B200_ALGO_ONESHOT) {
+  if (algo == B200_ALGO_LL) {
+    a.sym_off = -1;
+    allreduce_ll_kernel<T, OP><<<int((U + kThreads - 1) / kThreads), kThreads, 0, stream>>>(dc, a);
+  } else if (algo == B200_ALGO_ONESHOT) {
     a.sym_off = -1;
     int g = pick_blocks(c, (U + kThreads - 1) / kThreads, 32);
     allreduce_oneshot_kernel<T, OP><<<g, kThreads, 0, stream>>>(dc, a);
   } else {
     const size_t rows = (U + size_t(c->world) * kThreads - 1) / (size_t(c->world) * kThreads);
     int g = pick_blocks(c, rows, c->sm_count);
-    const size_t tiles = pipe_tiles(U, c->world);
-    // explicit opt-in only: measured slower than the phase kernel (profiles/r01/tune_w8_v2_graph.log)
-    const bool pipe = sym_off < 0 && c->params[B200_PARAM_PIPE_MIN_BYTES] >= 0 &&
-                      nbytes >= pipe_min_bytes(c) && tiles <= size_t(kMaxTiles);
     if (algo == B200_ALGO_NVLS) {
       a.red_ctas = nvls_ctas(c);
       if (sym_off >= 0) {  // nothing to stage: the whole launch is the reduce phase, which
@@ -195,11 +244,7 @@ static int launch_allreduce(b200_comm *c, const char *in, char *out, size_t nbyt
         a.red_ctas = 0;
       }
       if constexpr (Multimem<T>::kSum && (OP == B200_SUM || OP == B200_AVG)) {
-        const bool fused = sym_off < 0 && a.red_ctas == 0 && nbytes >= fused_min_bytes(c);
-        if (pipe) allreduce_pipe_kernel<T, OP><<<pick_blocks(c, tiles, c->sm_count), kPipeThreads, 0, stream>>>(dc, a);
-        else if (fused) allreduce_fused_kernel<T, OP><<<g, kThreads, 0, stream>>>(dc, a);
-        else if (c->params[B200_PARAM_NVLS_UNR] == 8) allreduce_twoshot_kernel<T, OP, true, 8><<<g, kThreads, 0, stream>>>(dc, a);
-        else allreduce_twoshot_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(dc, a);
+        allreduce_twoshot_kernel<T, OP, true><<<g, kThreads, 0, stream>>>(dc, a);
       } else {
         set_error("NVLS all-reduce supports SUM/AVG on f32/f16/bf16 only");
         return B200_ERR_UNSUPPORTED;
@@ -235,6 +280,12 @@ static bool nvls_pays_off(const b200_comm *c, size_t nbytes) {
 static int nvls_ctas(const b200_comm *c) {
   const long long v = c->params[B200_PARAM_NVLS_CTAS];
   return v > 0 ? int(v) : 0;
+}
+
+static size_t ll_limit(const b200_comm *c) {
+  const long long v = c->params[B200_PARAM_LL_MAX_BYTES];
+  const size_t lim = v >= 0 ? size_t(v) : (size_t(32) << 10);
+  return lim < kLLMaxPayload ? lim : kLLMaxPayload;
 }
 
 static size_t oneshot_limit(const b200_comm *c) {
@@ -295,10 +346,12 @@ extern "C" int b200_allreduce(b200_comm_t c, const void *in, void *out, size_t c
     const size_t nbytes = (total - done) < chunk_max ? (total - done) : chunk_max;
     int a = algo;
     if (a == B200_ALGO_AUTO) {
-      if (sym_off < 0 && nbytes <= oneshot_limit(c)) a = B200_ALGO_ONESHOT;
+      if (nbytes <= ll_limit(c)) a = B200_ALGO_LL;
+      else if (sym_off < 0 && nbytes <= oneshot_limit(c)) a = B200_ALGO_ONESHOT;
       else if (c->mc_active && nvls_capable(dtype, op) && nvls_pays_off(c, nbytes)) a = B200_ALGO_NVLS;
       else a = B200_ALGO_TWOSHOT;
     }
+    if (a == B200_ALGO_LL && nbytes > kLLMaxPayload) a = B200_ALGO_ONESHOT;
     if (a == B200_ALGO_ONESHOT && nbytes > c->staging_bytes) a = B200_ALGO_TWOSHOT;
     const long long so = sym_off >= 0 ? sym_off + (long long)done : -1;
     B200_DISPATCH_DTYPE(dtype, T, B200_DISPATCH_OP(op, OP, {

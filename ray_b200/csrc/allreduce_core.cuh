@@ -24,14 +24,14 @@ __device__ __forceinline__ RowGeom make_rows(size_t U, int n) {
 
 // Reduce the units this rank owns across all n ranks' buffers at offset `off` of the data
 // region and publish the result into every rank's buffer at the same offset.
-template <typename T, int OP, bool NVLS, int NVLS_UNR = 4>
+template <typename T, int OP, bool NVLS>
 __device__ __forceinline__ void reduce_publish_rows(const DevComm &c, size_t off, const RowGeom &g,
                                                     size_t G = 0) {
   using Tr = Traits<T>;
   const int n = c.world, r = c.rank, t = threadIdx.x;
   if (G == 0) G = gridDim.x;  // CTAs [0, G) share the rows of this phase
   if (NVLS) {
-    constexpr int UNR = NVLS_UNR;
+    constexpr int UNR = 4;  // 8 in flight measured slower on 8 GPUs (profiles/r01/tune_w8_v2_graph.log)
     char *mc = c.mc_data + off;
     for (size_t row0 = blockIdx.x; row0 < g.R; row0 += G * UNR) {
       uint4 v[UNR];
@@ -99,20 +99,20 @@ __device__ __forceinline__ void reduce_publish_rows(const DevComm &c, size_t off
 // red_ctas CTAs only and the two synchronisations become grid-wide flag waits (the row -> CTA
 // mapping differs between the phases); otherwise CTA b only meets CTA b of its peers.
 // Returns false if a wait was abandoned (abort / watchdog).
-template <typename T, int OP, bool NVLS, int NVLS_UNR = 4>
+template <typename T, int OP, bool NVLS>
 __device__ __forceinline__ bool reduce_phase(const DevComm &c, uint32_t ep, size_t off, const RowGeom &g,
                                              int red_ctas) {
   if (red_ctas > 0 && red_ctas < int(gridDim.x)) {
     cta_signal_all(c, ep + 1);
     if (int(blockIdx.x) < red_ctas) {
       if (!cta_wait_grid(c, gridDim.x, ep + 1)) return false;
-      reduce_publish_rows<T, OP, NVLS, NVLS_UNR>(c, off, g, red_ctas);
+      reduce_publish_rows<T, OP, NVLS>(c, off, g, red_ctas);
       cta_signal_all(c, ep + 2);
     }
     return cta_wait_grid(c, red_ctas, ep + 2);
   }
   if (!cta_barrier_all(c, ep + 1)) return false;
-  reduce_publish_rows<T, OP, NVLS, NVLS_UNR>(c, off, g);
+  reduce_publish_rows<T, OP, NVLS>(c, off, g);
   return cta_barrier_all(c, ep + 2);
 }
 

@@ -152,7 +152,7 @@ constexpr uint32_t kVersion = 1;
 // unix-socket helpers
 // ---------------------------------------------------------------------------
 enum : uint32_t { OP_GET_FD = 1, OP_AGREE = 2 };
-enum : uint32_t { FD_DATA = 0, FD_SIG = 1, FD_INBOX = 2, FD_MC = 3 };
+enum : uint32_t { FD_DATA = 0, FD_SIG = 1, FD_INBOX = 2, FD_MC = 3, FD_LL = 4 };
 struct Req {
   uint32_t magic;
   uint32_t op;
@@ -279,6 +279,7 @@ static void server_loop(b200_comm *c) {
           case FD_SIG: fd = c->sig.own_fd; break;
           case FD_INBOX: fd = c->inbox.own_fd; break;
           case FD_MC: fd = c->mc_fd; break;
+          case FD_LL: fd = c->ll.own_fd; break;
           default: break;
         }
       }
@@ -443,6 +444,7 @@ b200::DevComm b200_comm::dev() const {
     d.data[p] = reinterpret_cast<char *>(data.va[p]);
     d.sig[p] = reinterpret_cast<uint32_t *>(sig.va[p]);
     d.inbox[p] = reinterpret_cast<char *>(inbox.va[p]);
+    d.ll[p] = reinterpret_cast<char *>(ll.va[p]);
   }
   d.mc_data = mc_active ? reinterpret_cast<char *>(mc_va) : nullptr;
   d.st = d_state;
@@ -537,6 +539,7 @@ int b200_comm_create(int world_size, int rank, int device, const b200_config_t *
   int rc = region_create(c, &c->data, 2 * c->staging_bytes + c->heap_bytes, gran);
   if (!rc) rc = region_create(c, &c->sig, kSigWords * sizeof(uint32_t), gran);
   if (!rc) rc = region_create(c, &c->inbox, size_t(kMaxRanks) * c->inbox_bytes, gran);
+  if (!rc) rc = region_create(c, &c->ll, kLLRegionBytes, gran);
   if (!rc) {
     cudaError_t e = cudaMalloc(&c->d_state, sizeof(LocalState));
     if (e == cudaSuccess) e = cudaMemset(c->d_state, 0, sizeof(LocalState));
@@ -663,6 +666,7 @@ int b200_comm_connect(b200_comm_t c, const void *blobs) {
     int rc = region_import(c, &c->data, p, FD_DATA, gran);
     if (!rc) rc = region_import(c, &c->sig, p, FD_SIG, gran);
     if (!rc) rc = region_import(c, &c->inbox, p, FD_INBOX, gran);
+    if (!rc) rc = region_import(c, &c->ll, p, FD_LL, gran);
     if (rc) return rc;
   }
 
@@ -765,6 +769,7 @@ int b200_comm_destroy(b200_comm_t c) {
   region_destroy(c, &c->data);
   region_destroy(c, &c->sig);
   region_destroy(c, &c->inbox);
+  region_destroy(c, &c->ll);
   if (c->d_state) cudaFree(c->d_state);
   if (c->h_abort) cudaFreeHost(c->h_abort);
   (void)cudaGetLastError();

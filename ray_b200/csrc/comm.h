@@ -48,7 +48,7 @@ struct b200_comm {
   size_t inbox_bytes = 0;    // per source
   size_t heap_used = 0;
 
-  b200::Region data, sig, inbox;
+  b200::Region data, sig, inbox, ll;
 
   // NVLS
   bool mc_supported = false;  // this device + config allow multicast
@@ -73,7 +73,7 @@ struct b200_comm {
 
   std::atomic<uint64_t> launches{0};
   int forced_blocks = 0;
-  long long params[B200_PARAM_COUNT] = {-1, -1, -1, -1, -1, -1};
+  long long params[B200_PARAM_COUNT] = {-1, -1, -1, -1};
   int sm_count = 148;
   std::atomic<bool> aborted{false};
   std::mutex mu;

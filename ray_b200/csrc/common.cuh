@@ -9,8 +9,8 @@
 //                    coll flags  [MAX_BLOCKS][MAX_RANKS]
 //                    p2p ready   [MAX_RANKS src][P2P_RINGS][P2P_SLOTS]
 //                    p2p ack     [MAX_RANKS dst][P2P_RINGS]
-//                    tile-in / tile-out flags [MAX_TILES][MAX_RANKS] (pipelined kernels)
 //   region "inbox" : [MAX_RANKS src] x inbox_bytes point-to-point landing area
+//   region "ll"    : [2][MAX_RANKS src][128 KiB] flag-in-data slots of the low-latency all-reduce
 //
 // Rank-local (cudaMalloc) state: launch counter, completion ticket, sticky status,
 // p2p sequence numbers.
@@ -34,15 +34,13 @@ constexpr int kP2PSlots = 4;      // chunks in flight per sub-ring
 constexpr size_t kSigCollFlags = 0;
 constexpr size_t kSigP2PReady = kSigCollFlags + size_t(kMaxBlocks) * kMaxRanks;
 constexpr size_t kSigP2PAck = kSigP2PReady + size_t(kMaxRanks) * kP2PRings * kP2PSlots;
-// per-tile flags of the pipelined (role-specialised) kernels: "tile staged on rank p" and
-// "rank p published its slice of the tile"
-constexpr int kMaxTiles = 32768;
-constexpr size_t kSigTileIn = kSigP2PAck + size_t(kMaxRanks) * kP2PRings;
-constexpr size_t kSigTileOut = kSigTileIn + size_t(kMaxTiles) * kMaxRanks;
-// row counters of the fused (interleaved) kernels: "rows staged" / "rows published" by CTA b of rank p
-constexpr size_t kSigRowsIn = kSigTileOut + size_t(kMaxTiles) * kMaxRanks;
-constexpr size_t kSigRowsOut = kSigRowsIn + size_t(kMaxBlocks) * kMaxRanks;
-constexpr size_t kSigWords = kSigRowsOut + size_t(kMaxBlocks) * kMaxRanks;
+constexpr size_t kSigWords = kSigP2PAck + size_t(kMaxRanks) * kP2PRings;
+
+// Low-latency (LL) region: [2 parities][kMaxRanks sources][kLLSlotBytes]; payload and flag share
+// each 8-byte word pair, so a message needs no separate barrier.
+constexpr size_t kLLMaxPayload = size_t(64) << 10;      // bytes of payload per rank per launch
+constexpr size_t kLLSlotBytes = 2 * kLLMaxPayload;      // every 4-byte word travels with a 4-byte flag
+constexpr size_t kLLRegionBytes = 2 * size_t(kMaxRanks) * kLLSlotBytes;
 
 // rank-local state words
 struct LocalState {
@@ -52,7 +50,6 @@ struct LocalState {
   uint32_t pad;
   uint32_t send_seq[kMaxRanks][kP2PRings];  // next chunk sequence to peer, per ring
   uint32_t recv_seq[kMaxRanks][kP2PRings];  // next chunk sequence from peer, per ring
-  uint32_t fused_rows[kMaxBlocks];          // rows ever processed by CTA b in fused kernels
 };
 
 // Passed by value to every kernel.
@@ -62,6 +59,7 @@ struct DevComm {
   char *data[kMaxRanks];      // peers' data region (index == rank: own)
   uint32_t *sig[kMaxRanks];   // peers' signal pad
   char *inbox[kMaxRanks];     // peers' inbox region
+  char *ll[kMaxRanks];        // peers' low-latency region
   char *mc_data;              // multicast alias of the data region (nullptr without NVLS)
   LocalState *st;             // rank-local state
   const volatile int *abort;  // host-mapped abort word

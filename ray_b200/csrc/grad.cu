@@ -10,8 +10,7 @@
 //   stage-out: read the reduced wire values, cast back to fp32, write the bucket
 //
 // With wire = bf16 the NVLink traffic and the staging traffic are halved.
-#include "allreduce_fused.cuh"
-#include "allreduce_pipe.cuh"
+#include "allreduce_core.cuh"
 
 namespace b200 {
 
@@ -139,34 +138,6 @@ __global__ void __launch_bounds__(kThreads, 1) grad_allreduce_kernel(DevComm c, 
   finish_launch(c);
 }
 
-// NVLS with the staging (scale + wire cast in, cast back out) interleaved row by row with the
-// switch reduction, see allreduce_fused.cuh
-template <typename W>
-__global__ void __launch_bounds__(kThreads, 1) grad_fused_kernel(DevComm c, GradArgs a) {
-  constexpr int E = Wire<W>::kElems;
-  const uint32_t launch = c.st->launch_ctr;
-  const RowGeom g = make_rows((a.count + E - 1) / E, c.world);
-  const size_t off = staging_slot_offset(launch, a.staging_bytes);
-  const bool al = is_aligned16(a.grad);
-  allreduce_fused_nvls<W, B200_SUM>(
-      c, off, g, [&](size_t u) { return load_grad_unit<W>(a.grad, u, a.count, a.scale, al); },
-      [&](size_t u, uint4 v) { store_grad_unit<W>(a.grad, u, a.count, al, v); });
-  finish_launch(c);
-}
-
-template <typename W>
-__global__ void __launch_bounds__(kPipeThreads, 1) grad_pipe_kernel(DevComm c, GradArgs a) {
-  constexpr int E = Wire<W>::kElems;
-  const uint32_t launch = c.st->launch_ctr;
-  const size_t off = staging_slot_offset(launch, a.staging_bytes);
-  const bool al = is_aligned16(a.grad);
-  allreduce_pipelined_nvls<W, B200_SUM>(
-      c, launch * 4u + 1u, off, (a.count + E - 1) / E,
-      [&](size_t u) { return load_grad_unit<W>(a.grad, u, a.count, a.scale, al); },
-      [&](size_t u, uint4 v) { store_grad_unit<W>(a.grad, u, a.count, al, v); });
-  finish_launch_pipe(c);
-}
-
 // world == 1: the same arithmetic without any peer (scale, round-trip through the wire type).
 template <typename W>
 __global__ void grad_local_kernel(GradArgs a) {
@@ -191,22 +162,9 @@ static int launch_grad(b200_comm *c, GradArgs a, cudaStream_t stream) {
   int g = pick_blocks(c, rows, c->sm_count);
   const long long min_world = c->params[B200_PARAM_NVLS_MIN_WORLD] >= 0 ? c->params[B200_PARAM_NVLS_MIN_WORLD] : 3;
   const bool nvls = c->mc_active && c->world >= min_world;
-  const size_t tiles = pipe_tiles(U, c->world);
   if (!nvls) a.red_ctas = 0;  // peer-load reducers want the whole grid
-  const size_t fused_min = c->params[B200_PARAM_FUSED_MIN_BYTES] >= 0
-                               ? size_t(c->params[B200_PARAM_FUSED_MIN_BYTES]) : (size_t(4) << 20);
-  // The warp-specialised pipelined variant measured slower than the phase kernel on 8 GPUs
-  // (profiles/r01/tune_w8_v2_graph.log); it only runs when explicitly enabled.
-  if (nvls && c->params[B200_PARAM_PIPE_MIN_BYTES] >= 0 && U * 16 >= pipe_min_bytes(c) &&
-      tiles <= size_t(kMaxTiles)) {
-    grad_pipe_kernel<W><<<pick_blocks(c, tiles, c->sm_count), kPipeThreads, 0, stream>>>(c->dev(), a);
-  } else if (nvls && a.red_ctas == 0 && U * 16 >= fused_min) {
-    grad_fused_kernel<W><<<g, kThreads, 0, stream>>>(c->dev(), a);
-  } else if (nvls) {
-    grad_allreduce_kernel<W, true><<<g, kThreads, 0, stream>>>(c->dev(), a);
-  } else {
-    grad_allreduce_kernel<W, false><<<g, kThreads, 0, stream>>>(c->dev(), a);
-  }
+  if (nvls) grad_allreduce_kernel<W, true><<<g, kThreads, 0, stream>>>(c->dev(), a);
+  else grad_allreduce_kernel<W, false><<<g, kThreads, 0, stream>>>(c->dev(), a);
   B200_LAUNCH_CHECK(c);
   return B200_OK;
 }

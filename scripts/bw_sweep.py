@@ -17,7 +17,8 @@ import torch
 from ray_b200 import _native as N
 from ray_b200.testing import LocalGroup
 
-ALGOS = {"auto": N.ALGO_AUTO, "oneshot": N.ALGO_ONESHOT, "twoshot": N.ALGO_TWOSHOT, "nvls": N.ALGO_NVLS}
+ALGOS = {"auto": N.ALGO_AUTO, "oneshot": N.ALGO_ONESHOT, "twoshot": N.ALGO_TWOSHOT, "nvls": N.ALGO_NVLS,
+         "ll": N.ALGO_LL}
 
 
 def time_graphs(g, make_call, iters, reps=3):
@@ -66,10 +67,7 @@ def main():
     ap.add_argument("--op", default="allreduce")
     ap.add_argument("--dtype", default="float32")
     ap.add_argument("--symm", action="store_true", help="operands in the symmetric heap (zero copy)")
-    ap.add_argument("--pipe-min", type=int, default=-1, help="B200_PARAM_PIPE_MIN_BYTES (-1 default, huge = off)")
     ap.add_argument("--nvls-min-world", type=int, default=-1)
-    ap.add_argument("--nvls-unr", type=int, default=-1)
-    ap.add_argument("--fused-min", type=int, default=-1, help="B200_PARAM_FUSED_MIN_BYTES (huge = off)")
     ap.add_argument("--nvls-ctas", default="-1", help="comma list of CTA counts for the NVLS reduce phase")
     args = ap.parse_args()
     n = args.world
@@ -79,10 +77,7 @@ def main():
     print(f"# world={n} devices={g.devices} shared={g.shared_gpu} multicast={g.has_multicast} op={args.op} "
           f"dtype={args.dtype} symm={args.symm}")
     for c in g.comms:
-        c.set_param(N.PARAM_PIPE_MIN_BYTES, args.pipe_min)
         c.set_param(N.PARAM_NVLS_MIN_WORLD, args.nvls_min_world)
-        c.set_param(N.PARAM_NVLS_UNR, args.nvls_unr)
-        c.set_param(N.PARAM_FUSED_MIN_BYTES, args.fused_min)
     size = args.min
     es = torch.empty((), dtype=dtype).element_size()
     while size <= args.max:
@@ -99,6 +94,8 @@ def main():
                 if algo == N.ALGO_NVLS and not g.has_multicast:
                     continue
                 if algo == N.ALGO_ONESHOT and size > (8 << 20):
+                    continue
+                if algo == N.ALGO_LL and size > (64 << 10):
                     continue
                 if args.symm:
                     for c in g.comms:
@@ -133,7 +130,7 @@ def main():
                 torch.cuda.synchronize()
                 us = time_graphs(g, call, iters)
                 algbw = size / us / 1e3
-                print(f"{args.op} {size:>11d} B  algo={aname:8s} blocks={blocks:3d} nvls_ctas={nctas:3d} pipe_min={args.pipe_min:<3d} fused_min={args.fused_min:<11d} {us:10.2f} us  "
+                print(f"{args.op} {size:>11d} B  algo={aname:8s} blocks={blocks:3d} nvls_ctas={nctas:3d} {us:10.2f} us  "
                       f"algbw={algbw:8.1f} GB/s  busbw={algbw * factor:8.1f} GB/s", flush=True)
                 del xs
         size *= args.step

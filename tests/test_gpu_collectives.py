@@ -63,7 +63,7 @@ def groups(native_lib):
 def _algos(g):
     from ray_b200 import _native as N
 
-    out = [("oneshot", N.ALGO_ONESHOT), ("twoshot", N.ALGO_TWOSHOT), ("auto", N.ALGO_AUTO)]
+    out = [("ll", N.ALGO_LL), ("oneshot", N.ALGO_ONESHOT), ("twoshot", N.ALGO_TWOSHOT), ("auto", N.ALGO_AUTO)]
     if g.has_multicast:
         out.append(("nvls", N.ALGO_NVLS))
     return out
@@ -126,7 +126,9 @@ def test_allreduce_ragged_sizes_and_unaligned_views(groups, world):
 
     for numel in (1, 3, 4, 5, 127, 4096, 4097, (1 << 18) + 13):
         for dtype in (torch.float32, torch.int32, torch.uint8, torch.int64, torch.bfloat16):
-            for algo in (N.ALGO_ONESHOT, N.ALGO_TWOSHOT):
+            for algo in (N.ALGO_LL, N.ALGO_ONESHOT, N.ALGO_TWOSHOT):
+                if algo == N.ALGO_LL and numel * torch.empty((), dtype=dtype).element_size() > (64 << 10):
+                    continue
                 gen = torch.Generator().manual_seed(numel)
                 hi = 16 if dtype == torch.bfloat16 else 100  # keep bf16 sums exactly representable
                 base = [torch.randint(0, hi, (numel + 3,), generator=gen).to(dtype) for _ in range(world)]
@@ -328,7 +330,7 @@ def test_fused_gradient_sync_matches_ddp_arithmetic(groups, world, wire):
         for o in outs[1:]:
             assert np.array_equal(o, outs[0])
         if g.has_multicast and world > 2:
-            tol = {"f32": 1e-6, "bf16": 2.0 ** -8, "f16": 2.0 ** -11}[wire]
+            tol = {"f32": 1e-6, "bf16": 2.0 ** -6, "f16": 2.0 ** -9}[wire]  # switch rounds partial sums
             bound = tol * (np.abs(want) + np.sum([np.abs(x.numpy()) for x in grads], axis=0) / world) + 1e-30
             assert np.all(np.abs(outs[0] - want) <= bound)
         else:
@@ -445,116 +447,40 @@ def test_multi_tensor_allreduce_single_launch(groups, world):
         g.comms[0].allreduce_multi([torch.ones(2, device=g.device(0)), torch.ones(2, device=g.device(0)).half()])
 
 
-@pytest.mark.parametrize("world", [2, 3, 8])
-def test_pipelined_role_specialised_kernels_match_oracle(groups, world):
-    """The flag-pipelined large-message kernels (stagers-in / reducers / stagers-out running
-    concurrently) must produce exactly what the phase-by-phase kernels produce."""
-    from ray_b200 import _native as N
-
-    g = groups(world)
-    for c in g.comms:
-        c.set_param(N.PARAM_PIPE_MIN_BYTES, 64 << 10)
-        c.set_param(N.PARAM_NVLS_MIN_WORLD, 2)  # exercise the NVLS kernels whenever multicast exists
-    try:
-        algos = [N.ALGO_TWOSHOT] + ([N.ALGO_NVLS] if g.has_multicast else [])
-        for numel in (16 << 10, (1 << 20) + 77, (3 << 20) + 5):  # last one: chunked over 8 MiB slots
-            ins = [np.random.default_rng(100 * numel + r).standard_normal(numel).astype(np.float32)
-                   for r in range(world)]
-            want = O.reduce_rank_ascending(ins, O.SUM)
-            for algo in algos:
-                xs = [torch.from_numpy(ins[r].copy()).to(g.device(r)) for r in range(world)]
-                before = g.comms[0].launch_count
-                g.run(lambda c, r: c.allreduce(xs[r], N.SUM, algo=algo))
-                assert g.comms[0].launch_count > before
-                for r in range(world):
-                    got = xs[r].cpu().numpy()
-                    if algo == N.ALGO_NVLS and world > 2:
-                        bound = 1e-6 * np.sum([np.abs(i) for i in ins], axis=0) + 1e-30
-                        assert np.all(np.abs(got - want) <= bound)
-                    else:
-                        assert np.array_equal(got, want), (numel, algo)
-            # integers through the peer-load reducers, MAX op, ragged tail
-            ints = [np.random.default_rng(numel + r).integers(-1000, 1000, numel + 3).astype(np.int32)
-                    for r in range(world)]
-            xs = [torch.from_numpy(ints[r].copy()).to(g.device(r)) for r in range(world)]
-            g.run(lambda c, r: c.allreduce(xs[r], N.MAX, algo=N.ALGO_TWOSHOT))
-            for r in range(world):
-                assert np.array_equal(xs[r].cpu().numpy(), O.reduce_rank_ascending(ints, O.MAX))
-        # fused gradient kernel, bf16 wire
-        numel = (2 << 20) + 9
-        grads = [np.random.default_rng(r).standard_normal(numel).astype(np.float32) for r in range(world)]
-        dev = [torch.from_numpy(grads[r].copy()).to(g.device(r)) for r in range(world)]
-        g.run(lambda c, r: c.grad_allreduce(dev[r], 1.0 / world, torch.bfloat16))
-        want = O.ddp_grad_sync(grads, "bf16")[0]
-        for r in range(world):
-            got = dev[r].cpu().numpy()
-            if g.has_multicast:
-                assert np.all(np.abs(got - want) <= 2.0 ** -7 * (np.abs(want) + 1e-3))
-            else:
-                assert np.array_equal(got, want)
-        # back-to-back pipelined launches (slot rotation + monotonic tile flags)
-        x = [torch.ones(1 << 20, device=g.device(r)) for r in range(world)]
-        for _ in range(5):
-            g.run(lambda c, r: c.allreduce(x[r], N.SUM, algo=N.ALGO_TWOSHOT))
-        assert torch.all(x[0] == float(world) ** 5)
-    finally:
-        for c in g.comms:
-            c.set_param(N.PARAM_PIPE_MIN_BYTES, -1)
-            c.set_param(N.PARAM_NVLS_MIN_WORLD, -1)
-
-
-@pytest.mark.parametrize("world", [2, 3, 4, 8])
-def test_fused_interleaved_nvls_kernels_match_oracle(groups, world):
-    """The interleaved staged NVLS kernels (allreduce_fused.cuh): multi-row pipelines per CTA,
-    ragged tails, chunking across staging slots, back-to-back launches, fused gradient variant.
-    Needs the multicast mapping, i.e. one GPU per rank."""
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_nvls_kernels_on_real_multicast_hardware(groups, world):
+    """Exercises every NVLS entry (all-reduce staged / zero-copy / decoupled reduce CTAs, fused
+    gradient, multi-tensor, broadcast) when the box has one GPU per rank."""
     from ray_b200 import _native as N
 
     g = groups(world)
     if not g.has_multicast:
         pytest.skip("NVLS needs one GPU per rank")
     for c in g.comms:
-        c.set_param(N.PARAM_FUSED_MIN_BYTES, 0)
         c.set_param(N.PARAM_NVLS_MIN_WORLD, 2)
-        c.set_blocks(5)  # few CTAs -> many rows per CTA even for small tensors
     try:
-        for numel in (1, 2049, (1 << 18) + 3, (3 << 20) + 5):
-            ins = [np.random.default_rng(numel + r).standard_normal(numel).astype(np.float32) for r in range(world)]
-            want = O.reduce_rank_ascending(ins, O.SUM)
-            bound = 1e-6 * np.sum([np.abs(i) for i in ins], axis=0) + 1e-30
-            xs = [torch.from_numpy(ins[r].copy()).to(g.device(r)) for r in range(world)]
-            g.run(lambda c, r: c.allreduce(xs[r], N.SUM, algo=N.ALGO_NVLS))
-            outs = [x.cpu().numpy() for x in xs]
-            for o in outs:
-                assert np.array_equal(o, outs[0])
-                if world == 2:
-                    assert np.array_equal(o, want)
-                else:
-                    assert np.all(np.abs(o - want) <= bound)
-            # exact integers carried in fp32 / bf16: every rank, every element
-            ints = [torch.randint(-8, 8, (numel,), generator=torch.Generator().manual_seed(numel + r)).float()
-                    for r in range(world)]
-            for dt in (torch.float32, torch.bfloat16):
-                dev = [i.to(dt).to(g.device(r)) for r, i in enumerate(ints)]
-                for _ in range(3):  # back to back: slot rotation + cumulative row counters
+        for ctas in (-1, 8):
+            for c in g.comms:
+                c.set_param(N.PARAM_NVLS_CTAS, ctas)
+            for numel in (1, 4099, (3 << 20) + 5):
+                ints = [torch.randint(-8, 8, (numel,), generator=torch.Generator().manual_seed(numel + r)).float()
+                        for r in range(world)]
+                want = torch.stack(ints).sum(0)
+                for dt in (torch.float32, torch.bfloat16, torch.float16):
+                    dev = [i.to(dt).to(g.device(r)) for r, i in enumerate(ints)]
                     g.run(lambda c, r: c.allreduce(dev[r], N.SUM, algo=N.ALGO_NVLS))
-                    g.run(lambda c, r: dev[r].div_(world))
-                want_i = torch.stack(ints).sum(0) / world
-                for _ in range(2):
-                    want_i = want_i  # mean of identical values stays put after the first round
-                first = torch.stack(ints).sum(0) / world
+                    for r in range(world):
+                        assert torch.equal(dev[r].float().cpu(), want), (ctas, numel, dt)
+                grads = [i.clone().to(g.device(r)) for r, i in enumerate(ints)]
+                g.run(lambda c, r: c.grad_allreduce(grads[r], 1.0 / world, torch.bfloat16))
                 for r in range(world):
-                    assert torch.equal(dev[r].float().cpu(), first.to(dt).float()), (numel, dt)
-            grads = [np.random.default_rng(7 * numel + r).standard_normal(numel).astype(np.float32)
-                     for r in range(world)]
-            dev = [torch.from_numpy(grads[r].copy()).to(g.device(r)) for r in range(world)]
-            g.run(lambda c, r: c.grad_allreduce(dev[r], 1.0 / world, torch.bfloat16))
-            want_g = O.ddp_grad_sync(grads, "bf16")[0]
-            for r in range(world):
-                got = dev[r].cpu().numpy()
-                assert np.all(np.abs(got - want_g) <= 2.0 ** -7 * (np.abs(want_g) + np.sum(np.abs(grads), axis=0) / world))
+                    assert torch.equal(grads[r].cpu(), (want / world).to(torch.bfloat16).float())
+        for c in g.comms:
+            c.set_param(N.PARAM_NVLS_CTAS, -1)
+        xs = [torch.full((1 << 20,), float(r), device=g.device(r)) for r in range(world)]
+        g.run(lambda c, r: c.broadcast(xs[r], world - 1))
+        assert all(torch.all(x == world - 1) for x in xs)
     finally:
         for c in g.comms:
-            c.set_param(N.PARAM_FUSED_MIN_BYTES, -1)
             c.set_param(N.PARAM_NVLS_MIN_WORLD, -1)
-            c.set_blocks(0)
+            c.set_param(N.PARAM_NVLS_CTAS, -1)
