@@ -139,13 +139,29 @@ __global__ void __launch_bounds__(kThreads, 1) grad_allreduce_kernel(DevComm c, 
 }
 
 // world == 1: the same arithmetic without any peer (scale, round-trip through the wire type).
+// Pure HBM streaming (8 B per element): 4 units per thread with all loads issued before the
+// first store, 256-thread CTAs, a few CTAs per SM.
+constexpr int kLocalThreads = 256;
+constexpr int kLocalUnroll = 4;
 template <typename W>
-__global__ void grad_local_kernel(GradArgs a) {
+__global__ void __launch_bounds__(kLocalThreads) grad_local_kernel(GradArgs a) {
   constexpr int E = Wire<W>::kElems;
   const size_t U = (a.count + E - 1) / E;
   const bool al = is_aligned16(a.grad);
-  for (size_t u = size_t(blockIdx.x) * blockDim.x + threadIdx.x; u < U; u += size_t(gridDim.x) * blockDim.x)
-    store_grad_unit<W>(a.grad, u, a.count, al, load_grad_unit<W>(a.grad, u, a.count, a.scale, al));
+  const size_t stride = size_t(gridDim.x) * kLocalThreads * kLocalUnroll;
+  for (size_t u0 = size_t(blockIdx.x) * kLocalThreads * kLocalUnroll + threadIdx.x; u0 < U; u0 += stride) {
+    uint4 w[kLocalUnroll];
+#pragma unroll
+    for (int k = 0; k < kLocalUnroll; ++k) {
+      const size_t u = u0 + size_t(k) * kLocalThreads;
+      if (u < U) w[k] = load_grad_unit<W>(a.grad, u, a.count, a.scale, al);
+    }
+#pragma unroll
+    for (int k = 0; k < kLocalUnroll; ++k) {
+      const size_t u = u0 + size_t(k) * kLocalThreads;
+      if (u < U) store_grad_unit<W>(a.grad, u, a.count, al, w[k]);
+    }
+  }
 }
 
 template <typename W>
@@ -153,8 +169,9 @@ static int launch_grad(b200_comm *c, GradArgs a, cudaStream_t stream) {
   constexpr int E = Wire<W>::kElems;
   const size_t U = (a.count + E - 1) / E;
   if (c->world == 1) {
-    int g = pick_blocks(c, (U + kThreads - 1) / kThreads, 4 * c->sm_count);
-    grad_local_kernel<W><<<g, kThreads, 0, stream>>>(a);
+    const size_t per_cta = size_t(kLocalThreads) * kLocalUnroll;
+    int g = pick_blocks(c, (U + per_cta - 1) / per_cta, 8 * c->sm_count);
+    grad_local_kernel<W><<<g, kLocalThreads, 0, stream>>>(a);
     B200_LAUNCH_CHECK(c);
     return B200_OK;
   }
