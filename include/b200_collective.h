@@ -213,7 +213,7 @@ typedef enum {
   B200_PARAM_ONESHOT_MAX_BYTES = 0, /* all-reduce messages up to this size use the one-shot kernel */
   B200_PARAM_NVLS_MIN_WORLD = 1,    /* AUTO uses the NVLS kernels from this world size on (default 3) */
   B200_PARAM_NVLS_CTAS = 2,         /* CTAs of the NVSwitch reduce phase: zero-copy default 64, staged default all */
-  B200_PARAM_LL_MAX_BYTES = 3,      /* all-reduce messages up to this size use the LL kernel (default 32 KiB) */
+  B200_PARAM_LL_MAX_BYTES = 3,      /* all-reduce messages up to this size use the LL kernel (default 32 KiB / 2 ranks ... 4 KiB / 8 ranks) */
   B200_PARAM_COUNT = 4
 } b200_param_t;
 int b200_comm_set_param(b200_comm_t comm, int param, long long value);

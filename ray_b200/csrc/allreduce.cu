@@ -282,9 +282,11 @@ static int nvls_ctas(const b200_comm *c) {
   return v > 0 ? int(v) : 0;
 }
 
+// LL pays n-1 flag-doubled pushes per rank: measured break-even against the one-shot kernel is
+// ~32 KiB with 2 ranks and ~4 KiB with 8 (profiles/r01/final_w8_graph_sweeps.log).
 static size_t ll_limit(const b200_comm *c) {
   const long long v = c->params[B200_PARAM_LL_MAX_BYTES];
-  const size_t lim = v >= 0 ? size_t(v) : (size_t(32) << 10);
+  const size_t lim = v >= 0 ? size_t(v) : (size_t(64) << 10) / size_t(c->world) / (c->world > 4 ? 2 : 1);
   return lim < kLLMaxPayload ? lim : kLLMaxPayload;
 }
 
