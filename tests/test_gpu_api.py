@@ -252,3 +252,41 @@ def test_declarative_group_and_env_var_creation(workers, monkeypatch):
     assert w.run(f) == [1, 0]
     assert torch.all(bufs[0] == 2)
     w.destroy("decl")
+
+
+def test_rdt_tensor_transport_over_b200_group(workers):
+    """Boundary B3: TensorTransportManager contract (python/ray/experimental/rdt/
+    tensor_transport_manager.py:37-224) mapped onto send/recv of a B200 group, as the reference's
+    CollectiveTensorTransport does for NCCL (collective_tensor_transport.py:124-176)."""
+    from ray_b200.rdt import B200CommunicatorMetadata, B200TensorTransport
+
+    w = workers(2)
+    w.init("rdt-group")
+    tr = B200TensorTransport()
+    assert tr.tensor_transport_backend() == "B200" and not tr.is_one_sided() and tr.can_abort_transport()
+    B200TensorTransport.group_resolver = staticmethod(
+        lambda src, dst: ("rdt-group", int(src[-1]), int(dst[-1])))
+    try:
+        assert tr.actor_has_tensor_transport("actor0")
+        meta_c = tr.get_communicator_metadata("actor0", "actor1", "B200")
+        assert isinstance(meta_c, B200CommunicatorMetadata) and (meta_c.src_rank, meta_c.dst_rank) == (0, 1)
+        payload = [torch.randn(17, 3), torch.arange(1000, dtype=torch.float32), torch.randn(5).to(torch.float16)]
+        sent = [t.to(w.dev(0)) for t in payload]
+        meta_t = tr.extract_tensor_transport_metadata("obj-1", sent)
+        assert meta_t.tensor_device == "cuda" and len(meta_t.tensor_meta) == 3
+        with pytest.raises(ValueError, match="same device type"):
+            tr.extract_tensor_transport_metadata("obj-2", [sent[0], torch.ones(1)])
+
+        def f(r):
+            if r == 0:
+                tr.send_multiple_tensors(sent, meta_t, meta_c)
+                return None
+            got = tr.recv_multiple_tensors("obj-1", meta_t, meta_c)
+            torch.cuda.current_stream().synchronize()
+            return [g.cpu() for g in got]
+
+        got = w.run(f)[1]
+        assert all(torch.equal(g, p) for g, p in zip(got, payload))
+        tr.garbage_collect("obj-1", meta_t, sent)
+    finally:
+        B200TensorTransport.group_resolver = None
