@@ -260,6 +260,22 @@ class B200Communicator(Communicator):
         code = _cgraph_op_code(op)
         self._collective(send_buf, recv_buf, lambda c: c.reducescatter_from(recv_buf, send_buf, code))
 
+    def allreduce_multi(self, tensors, op=0) -> None:
+        """In-place all-reduce of a list of same-dtype tensors as ONE message in ONE launch (the
+        multi-tensor ``allreduce.bind`` case, dag/collective_node.py:212-232)."""
+        code = _cgraph_op_code(op)
+        comm = self._check_open()
+        if len({t.dtype for t in tensors}) > 1:
+            raise ValueError(f"Expected all input tensors to have the same dtype, but got {[t.dtype for t in tensors]}")
+        try:
+            with torch.cuda.stream(self._cuda_stream):
+                comm.allreduce_multi(list(tensors), code)
+            self._cuda_stream.synchronize()
+            if self._closed or comm.status() != 0:
+                raise RayChannelError("B200 group has been destroyed during a collective operation.")
+        except N.B200AbortedError as e:
+            raise RayChannelError(str(e)) from e
+
     # ------------------------------------------------------------------ lifecycle
     def destroy(self) -> None:
         if self._closed:

@@ -275,7 +275,6 @@ struct PlainTraits {
 #pragma unroll
     for (int i = 0; i < LANES; ++i) a.v[i] = a.v[i] / S(n);
   }
-  static __device__ __forceinline__ void scale(Acc &, float) {}
 };
 
 template <> struct Traits<float> : PlainTraits<float, 4> {};

@@ -25,11 +25,7 @@ def time_graphs(g, make_call, iters, reps=3):
     """Capture `iters` launches per rank into one graph per rank; replay; return us per launch
     (max over ranks, best of reps)."""
     graphs = []
-    for r, c in enumerate(g.comms):
-        torch.cuda.set_device(g.devices[r])
-        s = g.streams[r]
-        # one eager warm-up outside capture (module load, lazy init)
-    g.run(lambda c, r: make_call(c, r))
+    g.run(lambda c, r: make_call(c, r))  # one eager warm-up outside capture (module load, lazy init)
     for r, c in enumerate(g.comms):
         torch.cuda.set_device(g.devices[r])
         gr = torch.cuda.CUDAGraph()

@@ -252,3 +252,37 @@ def test_destroy_from_another_thread_unblocks_recv_and_raises(actors):
         reader.send(torch.ones(1, device=a.dev(1)), 0)
     with pytest.raises(RayChannelError):
         reader.allreduce(torch.ones(1, device=a.dev(1)), torch.ones(1, device=a.dev(1)), 0)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_collective_operation_execute_matches_oracle(actors, world):
+    """_CollectiveOperation.execute (dag/collective_node.py:176-248) through the B200
+    communicator: output allocation, dim-0 layouts, multi-tensor all-reduce in one launch."""
+    from ray_b200.channel import AllGatherOp, AllReduceOp, ReduceScatterOp, execute_collective
+
+    a = actors(world)
+    d0 = 2 * world
+    xs = [torch.randn(d0, 4, generator=torch.Generator().manual_seed(r)) for r in range(world)]
+    ys = [torch.randn(33, generator=torch.Generator().manual_seed(50 + r)) for r in range(world)]
+
+    def f(r, c):
+        x, y = xs[r].to(a.dev(r)), ys[r].to(a.dev(r))
+        before = c.comm.launch_count
+        multi = execute_collective(c, AllReduceOp(), x, y)
+        launches = c.comm.launch_count - before
+        return (execute_collective(c, AllGatherOp(), x).cpu().numpy(),
+                execute_collective(c, AllReduceOp(), x).cpu().numpy(),
+                execute_collective(c, ReduceScatterOp(), x).cpu().numpy(),
+                [m.cpu().numpy() for m in multi], launches, x.cpu().numpy())
+
+    res = a.run(f)
+    np_x, np_y = [x.numpy() for x in xs], [y.numpy() for y in ys]
+    for r in range(world):
+        ag, ar, rs, multi, launches, x_after = res[r]
+        assert np.array_equal(ag, O.cgraph_allgather(np_x)[r])
+        assert np.array_equal(ar, O.cgraph_allreduce(np_x, 0)[r])
+        assert np.array_equal(rs, O.cgraph_reducescatter(np_x, 0)[r])
+        assert np.array_equal(multi[0], O.cgraph_allreduce(np_x, 0)[r])
+        assert np.array_equal(multi[1], O.cgraph_allreduce(np_y, 0)[r])
+        assert launches == 1, "the tensor list must be reduced by a single kernel launch"
+        assert np.array_equal(x_after, np_x[r]), "inputs of an out-of-place collective are untouched"
