@@ -33,8 +33,6 @@ def worker(rank, store_dir, out_path):
     comm = B200Communicator(2, "pingpong", None, ["w0", "w1"], None, False, FileStore(store_dir), rank,
                             inbox_bytes=64 << 20, staging_bytes=16 << 20)
     comm.initialize(rank)
-    fwd = TorchTensorAcceleratorChannel(comm, 0, [1], static_shape=True, direct_return=True)
-    back = TorchTensorAcceleratorChannel(comm, 1, [0], static_shape=True, direct_return=True)
     dist.init_process_group("nccl", init_method=f"file://{store_dir}/nccl_rdzv", rank=rank, world_size=2,
                             device_id=dev)
     alloc = lambda shape, dtype: torch.empty(shape, dtype=dtype, device=dev)  # noqa: E731
@@ -44,6 +42,9 @@ def worker(rank, store_dir, out_path):
         x = torch.ones(numel, dtype=torch.float16, device=dev)
         iters = 200 if nbytes <= (1 << 20) else (30 if nbytes <= (64 << 20) else 8)
         res = {"bytes": nbytes}
+        # _static_shape=True, _direct_return=True: metadata travels once per channel
+        fwd = TorchTensorAcceleratorChannel(comm, 0, [1], static_shape=True, direct_return=True)
+        back = TorchTensorAcceleratorChannel(comm, 1, [0], static_shape=True, direct_return=True)
         for name in ("b200_raw", "b200_channel", "nccl"):
             def one():
                 if name == "b200_raw":
