@@ -196,8 +196,7 @@ class B200Communicator(Communicator):
         if self._use_communication_streams:
             self._send_stream.synchronize()  # keep the host loop from running far ahead (nccl_group.py:167-174)
         try:
-            with torch.cuda.stream(self._send_stream):
-                comm.send(buf, peer_rank)
+            comm.send(buf, peer_rank, stream=self._send_stream)
         except N.B200AbortedError as e:
             raise RayChannelError(str(e)) from e
 
@@ -209,11 +208,9 @@ class B200Communicator(Communicator):
         try:
             if self._use_communication_streams:
                 self._recv_stream.synchronize()
-                with torch.cuda.stream(self._recv_stream):
-                    comm.recv(buf, peer_rank)
+                comm.recv(buf, peer_rank, stream=self._recv_stream)
             else:
-                with torch.cuda.stream(self._recv_stream):
-                    comm.recv(buf, peer_rank)
+                comm.recv(buf, peer_rank, stream=self._recv_stream)
                 # Buffer contents are undefined if the op was aborted: wait and re-check
                 # (nccl_group.py:232-240).
                 self._recv_stream.synchronize()

@@ -267,15 +267,20 @@ class B200Comm:
     def barrier(self) -> None:
         N.check(self._lib.b200_barrier(self._h, self._stream()))
 
-    def send(self, tensor: torch.Tensor, peer: int) -> None:
+    def send(self, tensor: torch.Tensor, peer: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Enqueue a send on ``stream`` (default: the current stream of this rank's device)."""
         _check_cuda_contiguous(tensor)
-        N.check(self._lib.b200_send(self._h, tensor.data_ptr(), tensor.numel() * tensor.element_size(),
-                                    int(peer), self._stream()))
+        st = self._lib.b200_send(self._h, tensor.data_ptr(), tensor.numel() * tensor.element_size(), int(peer),
+                                 stream.cuda_stream if stream is not None else self._stream())
+        if st:
+            N.check(st)
 
-    def recv(self, tensor: torch.Tensor, peer: int) -> None:
+    def recv(self, tensor: torch.Tensor, peer: int, stream: Optional[torch.cuda.Stream] = None) -> None:
         _check_cuda_contiguous(tensor)
-        N.check(self._lib.b200_recv(self._h, tensor.data_ptr(), tensor.numel() * tensor.element_size(),
-                                    int(peer), self._stream()))
+        st = self._lib.b200_recv(self._h, tensor.data_ptr(), tensor.numel() * tensor.element_size(), int(peer),
+                                 stream.cuda_stream if stream is not None else self._stream())
+        if st:
+            N.check(st)
 
     def grad_allreduce(self, grad: torch.Tensor, scale: float, wire_dtype: torch.dtype = torch.bfloat16) -> None:
         """Fused ``grad = sum_r wire(grad_r * scale)`` on a flat fp32 bucket."""

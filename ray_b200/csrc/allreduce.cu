@@ -132,13 +132,13 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_ll_kernel(DevComm c, AR
             if (lo.y == flag && lo.w == flag && hi.y == flag && hi.w == flag) break;
             if ((++spins & 0x3ff) == 0) {
               if (*c.abort != 0) {
-                atomicCAS(&c.st->status, 0, int(B200_ERR_ABORTED));
+                give_up(c, B200_ERR_ABORTED);
                 alive = false;
               }
               const unsigned long long now = globaltimer_ns();
               if (t0 == 0) t0 = now;
               else if (now - t0 > c.timeout_ns) {
-                atomicCAS(&c.st->status, 0, int(B200_ERR_TIMEOUT));
+                give_up(c, B200_ERR_TIMEOUT);
                 alive = false;
               }
             }

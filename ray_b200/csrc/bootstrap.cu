@@ -449,6 +449,7 @@ b200::DevComm b200_comm::dev() const {
   d.mc_data = mc_active ? reinterpret_cast<char *>(mc_va) : nullptr;
   d.st = d_state;
   d.abort = d_abort;
+  d.host_status = d_abort + 1;
   d.timeout_ns = (unsigned long long)(cfg.timeout_ms) * 1000000ull;
   d.inbox_bytes = inbox_bytes;
   return d;
@@ -543,9 +544,10 @@ int b200_comm_create(int world_size, int rank, int device, const b200_config_t *
   if (!rc) {
     cudaError_t e = cudaMalloc(&c->d_state, sizeof(LocalState));
     if (e == cudaSuccess) e = cudaMemset(c->d_state, 0, sizeof(LocalState));
-    if (e == cudaSuccess) e = cudaHostAlloc(&c->h_abort, sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostAlloc(&c->h_abort, 2 * sizeof(int), cudaHostAllocMapped);
     if (e == cudaSuccess) {
-      *c->h_abort = 0;
+      c->h_abort[0] = 0;  // abort request (host -> device)
+      c->h_abort[1] = 0;  // status mirror (device -> host)
       e = cudaHostGetDevicePointer(&c->d_abort, c->h_abort, 0);
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -734,14 +736,9 @@ int b200_comm_abort(b200_comm_t c) {
 int b200_comm_status(b200_comm_t c) {
   if (!c) return B200_ERR_INVALID;
   if (c->aborted.load()) return B200_ERR_ABORTED;
-  if (!c->d_state) return B200_ERR_INVALID;
-  int32_t st = 0;
-  cudaSetDevice(c->device);
-  if (cudaMemcpy(&st, &c->d_state->status, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess) {
-    set_error("status read failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return B200_ERR_CUDA;
-  }
-  return st;
+  if (!c->h_abort) return B200_ERR_INVALID;
+  // host-mapped mirror written by the kernel that gave up: no CUDA call on this path
+  return __atomic_load_n(&c->h_abort[1], __ATOMIC_ACQUIRE);
 }
 
 int b200_comm_destroy(b200_comm_t c) {

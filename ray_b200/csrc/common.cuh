@@ -63,6 +63,7 @@ struct DevComm {
   char *mc_data;              // multicast alias of the data region (nullptr without NVLS)
   LocalState *st;             // rank-local state
   const volatile int *abort;  // host-mapped abort word
+  volatile int *host_status;  // host-mapped mirror of LocalState::status (read without a CUDA call)
   unsigned long long timeout_ns;
   size_t inbox_bytes;         // per-source inbox size
 };
@@ -123,6 +124,15 @@ __device__ __forceinline__ void multimem_st(void *mc, uint4 v) {
                : "memory");
 }
 
+// A kernel that abandons a wait records why: sticky device word (first error wins) plus a
+// host-mapped mirror so b200_comm_status() is a plain host load.
+__device__ __forceinline__ void give_up(const DevComm &c, int code) {
+  if (atomicCAS(&c.st->status, 0, code) == 0) {
+    *c.host_status = code;
+    __threadfence_system();
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Cross-GPU CTA barrier.
 //
@@ -142,13 +152,13 @@ __device__ __forceinline__ bool wait_flag_ge(const DevComm &c, const uint32_t *f
     if (int32_t(v - epoch) >= 0) return true;
     if ((++spins & 0x3ff) == 0) {
       if (*c.abort != 0) {
-        atomicCAS(&c.st->status, 0, int(B200_ERR_ABORTED));
+        give_up(c, B200_ERR_ABORTED);
         return false;
       }
       unsigned long long now = globaltimer_ns();
       if (t0 == 0) t0 = now;
       else if (now - t0 > c.timeout_ns) {
-        atomicCAS(&c.st->status, 0, int(B200_ERR_TIMEOUT));
+        give_up(c, B200_ERR_TIMEOUT);
         return false;
       }
     }
@@ -196,14 +206,14 @@ __device__ __forceinline__ bool cta_wait_grid(const DevComm &c, int nb, uint32_t
         if (sleep_ns < 1024) sleep_ns <<= 1;
         if ((++spins & 0xff) == 0) {
           if (*c.abort != 0) {
-            atomicCAS(&c.st->status, 0, int(B200_ERR_ABORTED));
+            give_up(c, B200_ERR_ABORTED);
             ok = 0;
             break;
           }
           const unsigned long long now = globaltimer_ns();
           if (t0 == 0) t0 = now;
           else if (now - t0 > c.timeout_ns) {
-            atomicCAS(&c.st->status, 0, int(B200_ERR_TIMEOUT));
+            give_up(c, B200_ERR_TIMEOUT);
             ok = 0;
             break;
           }

@@ -22,8 +22,19 @@ namespace b200 {
 struct P2PArgs {
   char *buf;
   size_t nbytes;
+  size_t chunk;  // bytes per chunk of THIS message (<= slot size), same on both sides
   int peer;
 };
+
+// Chunk size is a pure function of the message size, so sender and receiver agree: big messages
+// use whole ring slots; mid-size ones are cut into kP2PRings pieces so that every CTA (one per
+// ring) carries one chunk and the message moves in parallel instead of through one CTA.
+inline size_t p2p_chunk_bytes(size_t nbytes, size_t slot_bytes) {
+  size_t c = (nbytes + kP2PRings - 1) / kP2PRings;
+  c = (c + 4095) & ~size_t(4095);
+  if (c < (size_t(16) << 10)) c = size_t(16) << 10;
+  return c < slot_bytes ? c : slot_bytes;
+}
 
 __device__ __forceinline__ bool cta_wait_flag(const DevComm &c, const uint32_t *flag, uint32_t target) {
   __shared__ int ok;
@@ -37,7 +48,8 @@ __global__ void __launch_bounds__(kThreads, 1) p2p_kernel(DevComm c, P2PArgs a) 
   const int me = c.rank, peer = a.peer;
   const int b = blockIdx.x, G = gridDim.x;
   const size_t ring_bytes = c.inbox_bytes / kP2PRings;
-  const size_t chunk = ring_bytes / kP2PSlots;
+  const size_t slot_bytes = ring_bytes / kP2PSlots;
+  const size_t chunk = a.chunk;
   const size_t nchunks = (a.nbytes + chunk - 1) / chunk;
   const bool al = is_aligned16(a.buf);
 
@@ -59,7 +71,7 @@ __global__ void __launch_bounds__(kThreads, 1) p2p_kernel(DevComm c, P2PArgs a) 
     const Units un = make_units(len);
     const size_t U = un.total();
     const uint32_t slot = seq % kP2PSlots;
-    char *slot_ptr = ring + size_t(slot) * chunk;
+    char *slot_ptr = ring + size_t(slot) * slot_bytes;
     char *user = a.buf + lo;
     if (SEND) {
       // slot free once the receiver consumed chunk (seq - kP2PSlots)
@@ -120,11 +132,11 @@ static int p2p_common(b200_comm *c, void *buf, size_t nbytes, int peer, cudaStre
     return B200_ERR_INVALID;
   }
   B200_CHECK_CUDA(cudaSetDevice(c->device));
-  const size_t chunk = c->inbox_bytes / kP2PRings / kP2PSlots;
+  const size_t chunk = p2p_chunk_bytes(nbytes, c->inbox_bytes / kP2PRings / kP2PSlots);
   const size_t nchunks = (nbytes + chunk - 1) / chunk;
   // Grid is a pure function of the message size so both sides pair CTA b with CTA b.
   int g = int(nchunks < size_t(kP2PRings) ? nchunks : size_t(kP2PRings));
-  P2PArgs a{static_cast<char *>(buf), nbytes, peer};
+  P2PArgs a{static_cast<char *>(buf), nbytes, chunk, peer};
   if (send) p2p_kernel<true><<<g, kThreads, 0, stream>>>(c->dev(), a);
   else p2p_kernel<false><<<g, kThreads, 0, stream>>>(c->dev(), a);
   B200_LAUNCH_CHECK(c);
