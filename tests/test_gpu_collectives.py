@@ -484,3 +484,24 @@ def test_nvls_kernels_on_real_multicast_hardware(groups, world):
         for c in g.comms:
             c.set_param(N.PARAM_NVLS_MIN_WORLD, -1)
             c.set_param(N.PARAM_NVLS_CTAS, -1)
+
+
+def test_allreduce_256MiB_exact_and_checksum_of_checksums(groups):
+    """BASELINE-size message (256 MiB per rank, 32 staging slots' worth of chunks): exact integer
+    pattern on every element, plus a size-independent property -- the checksum of the reduced
+    tensor equals the sum of the per-rank checksums (int64, no overflow)."""
+    g = groups(2)
+    numel = (256 << 20) // 4
+    xs = [(torch.arange(numel, dtype=torch.int32, device=g.device(r)) % 4093) * (r + 1) - 7 * r for r in range(2)]
+    sums = [int(x.to(torch.int64).sum().item()) for x in xs]
+    g.run(lambda c, r: c.allreduce(xs[r], 0))
+    want = (torch.arange(numel, dtype=torch.int32, device=g.device(0)) % 4093) * 3 - 7
+    for r in range(2):
+        assert torch.equal(xs[r].to(g.device(0)), want)
+        assert int(xs[r].to(torch.int64).sum().item()) == sum(sums)
+    del want
+    # send/recv of the same size: byte-exact round trip
+    a = torch.randint(0, 255, (256 << 20,), dtype=torch.uint8, device=g.device(0))
+    b = torch.empty_like(a, device=g.device(1))
+    g.run(lambda c, r: c.send(a, 1) if r == 0 else c.recv(b, 0))
+    assert torch.equal(a.to(g.device(1)) if a.device != b.device else a, b)
