@@ -14,7 +14,7 @@ node runs inside each actor's execution loop:
 """
 from __future__ import annotations
 
-from typing import Sequence, Tuple, Union
+from typing import Tuple, Union
 
 import torch
 

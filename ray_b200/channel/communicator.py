@@ -15,7 +15,7 @@ accepts the constructor arguments of torch_tensor_accelerator_channel.py:673-680
 from __future__ import annotations
 
 import uuid
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, Optional, Tuple
 
 import torch
 
