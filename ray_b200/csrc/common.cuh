@@ -27,7 +27,7 @@ namespace b200 {
 constexpr int kMaxRanks = B200_MAX_RANKS;
 constexpr int kMaxBlocks = 512;   // upper bound on collective grid size (flag rows)
 constexpr int kThreads = 512;     // CTA size of every collective kernel
-constexpr int kP2PRings = 32;     // independent sub-rings per ordered pair (one per CTA)
+constexpr int kP2PRings = 64;     // independent sub-rings per ordered pair (one per CTA)
 constexpr int kP2PSlots = 4;      // chunks in flight per sub-ring
 
 // signal pad offsets, in u32 words

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) p2p_kernel(DevComm c, P2PArgs a) 
     if (SEND) {
       // slot free once the receiver consumed chunk (seq - kP2PSlots)
       if (!cta_wait_flag(c, ack, seq + 1u - kP2PSlots)) break;
-      // 8 x 16 B per thread in flight: one CTA sustains ~40 GB/s, 32 rings saturate the link
+      // 8 x 16 B per thread in flight: one CTA sustains ~20 GB/s, so 64 rings are needed to saturate the link
       for (size_t u0 = threadIdx.x; u0 < U; u0 += size_t(kThreads) * 8) {
         uint4 v[8];
 #pragma unroll
