@@ -109,7 +109,10 @@ class TorchDistStore(Store):
     def get(self, key, timeout_s=180.0):
         import datetime
 
-        self._s.wait([key], datetime.timedelta(seconds=timeout_s))
+        try:
+            self._s.wait([key], datetime.timedelta(seconds=max(timeout_s, 0.001)))
+        except Exception as exc:  # torch raises DistStoreError / RuntimeError on expiry
+            raise TimeoutError(f"rendezvous key {key!r} never appeared in the torch store") from exc
         return bytes(self._s.get(key))
 
     def delete(self, key):

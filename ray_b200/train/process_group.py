@@ -123,8 +123,11 @@ class B200ProcessGroup(dist.ProcessGroup):
             if self._comm is None:
                 idx = device.index if device.index is not None else torch.cuda.current_device()
                 self._device = torch.device("cuda", idx)
-                st = TorchDistStore(dist.PrefixStore(f"b200pg{self._serial}/", self._store))
-                self._comm = B200Comm(self._size, self._rank, idx, store=st, group_name=f"pg{self._serial}",
+                # `self._store` is already scoped to this process group by torch (a PrefixStore per
+                # group), so the keys must NOT depend on per-process counters: ranks that are not
+                # members of every subgroup would otherwise disagree on the names.
+                st = TorchDistStore(dist.PrefixStore("b200comm/", self._store))
+                self._comm = B200Comm(self._size, self._rank, idx, store=st, group_name="pg",
                                       **self._comm_kwargs)
                 self._stream = torch.cuda.Stream(device=self._device)
             elif device.index is not None and device.index != self._device.index:
@@ -134,7 +137,7 @@ class B200ProcessGroup(dist.ProcessGroup):
     def _cpu_group(self):
         with self._lock:
             if self._gloo is None:
-                self._gloo = dist.ProcessGroupGloo(dist.PrefixStore(f"b200pg{self._serial}/gloo/", self._store),
+                self._gloo = dist.ProcessGroupGloo(dist.PrefixStore("b200gloo/", self._store),
                                                    self._rank, self._size, self._timeout)
             return self._gloo
 

@@ -168,3 +168,8 @@ def test_torch_dist_store_adapter():
     st = TorchDistStore(dist.HashStore())
     st.set("a", b"xyz")
     assert st.get("a") == b"xyz"
+    with pytest.raises(TimeoutError):
+        st.get("missing", timeout_s=0.0)
+    st.delete("a")
+    with pytest.raises(TimeoutError):
+        st.get("a", timeout_s=0.05)

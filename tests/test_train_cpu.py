@@ -35,6 +35,17 @@ def _worker(rank, world, init_file, out_dir):
     dist.all_gather_object(objs, {"rank": rank})
     assert [o["rank"] for o in objs] == [0, 1]
     dist.barrier()
+    # subgroups: rank 0 alone first (rank 1 is not a member), then both -- the second group must
+    # still rendezvous although the two ranks have created a different number of groups
+    solo = dist.new_group([0], backend="b200")
+    both = dist.new_group([0, 1], backend="b200")
+    if rank == 0:
+        s = torch.ones(2)
+        dist.all_reduce(s, group=solo)
+        assert torch.all(s == 1)
+    t = torch.ones(4) * (rank + 1)
+    dist.all_reduce(t, group=both)
+    assert torch.all(t == 3)
     assert pg.comm is None, "no CUDA communicator may be created for CPU-only traffic"
     dist.destroy_process_group()
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
