@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- TorchTrainer-shaped ResNet-50 DDP step (BASELINE.json configs[1]) on N B200s.
 
-    python bench.py --gpus 1 --steps 30 --warmup 5
+    python bench.py --gpus 1 --steps 50 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...   # the reference's CPU path (gloo DDP on host cores)
@@ -42,7 +42,7 @@ FLOPS_PER_SAMPLE = 24.6e9  # fwd+bwd, 224x224 (3 x 8.2 GFLOP)
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--steps", type=int, default=50)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference", "nccl"])
     p.add_argument("--batch", type=int, default=32, help="per-GPU batch")
