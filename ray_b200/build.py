@@ -65,7 +65,7 @@ def _compile_one(nvcc: str, src: str, verbose: bool) -> str:
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile (if needed) and return the path of libb200_collective.so."""
     BUILD_DIR.mkdir(parents=True, exist_ok=True)
-    stamp = BUILD_DIR / "digest.txt"
+    stamp = PKG_DIR / "libb200_collective.so.digest"  # next to the .so so it travels with it
     digest = _digest()
     if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == digest:
         return LIB_PATH
