@@ -80,7 +80,9 @@ typedef enum {
   B200_ALGO_ONESHOT = 1,  /* every rank reads all peers' staged inputs (latency path) */
   B200_ALGO_TWOSHOT = 2,  /* owner reduces its stripe from peer HBM, pushes result to all peers */
   B200_ALGO_NVLS = 3,     /* multimem.ld_reduce + multimem.st through the NVSwitch */
-  B200_ALGO_LL = 4        /* flag-in-data push, no barrier (<= 64 KiB) */
+  B200_ALGO_LL = 4,       /* flag-in-data push, no barrier (<= 64 KiB) */
+  B200_ALGO_PIPE = 5      /* chunk-pipelined: TMA copy-in | reduce | TMA copy-out roles in one launch
+                             (n == 2: one-shot push straight into the peer's slot) */
 } b200_algo_t;
 
 typedef struct {
@@ -214,7 +216,14 @@ typedef enum {
   B200_PARAM_NVLS_MIN_WORLD = 1,    /* AUTO uses the NVLS kernels from this world size on (default 3) */
   B200_PARAM_NVLS_CTAS = 2,         /* CTAs of the NVSwitch reduce phase: zero-copy default 64, staged default all */
   B200_PARAM_LL_MAX_BYTES = 3,      /* all-reduce messages up to this size use the LL kernel (default 32 KiB / 2 ranks ... 4 KiB / 8 ranks) */
-  B200_PARAM_COUNT = 4
+  B200_PARAM_PIPE_MIN_BYTES = 4,    /* AUTO uses the pipelined kernels from this size on (ordinary, 16-byte aligned tensors) */
+  B200_PARAM_PIPE_CHUNK_BYTES = 5,  /* pipeline chunk size (default 1 MiB; rounded up to 1 MiB multiples) */
+  B200_PARAM_PIPE_COPY_CTAS = 6,    /* CTAs per TMA copy role (power of two; default 8, push 16) */
+  B200_PARAM_PIPE_RED_CTAS = 7,     /* CTAs of the reduce role (default 48) */
+  B200_PARAM_PIPE_VARIANT = 8,      /* B200_ALGO_PIPE only: force 0 = push, 1 = NVLS roles, 2 = peer ld/st roles */
+  B200_PARAM_GRAD_LOCAL_UNROLL = 9, /* world 1 gradient kernel: 16-byte wire units per thread (1, 2, 4, 8) */
+  B200_PARAM_P2P_BULK_MIN_CHUNK = 10, /* send/recv: chunks from this size on move with the TMA bulk-copy kernel (0 = never; default 32 KiB) */
+  B200_PARAM_COUNT = 11
 } b200_param_t;
 int b200_comm_set_param(b200_comm_t comm, int param, long long value);
 

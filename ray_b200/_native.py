@@ -30,9 +30,11 @@ U8, I8, I32, U32, I64, U64, F16, BF16, F32, F64 = range(10)
 # reduce ops (b200_op_t) -- same numbering as ray.util.collective.types.ReduceOp
 SUM, PROD, MIN, MAX, AVG = range(5)
 # tuning parameters (b200_param_t)
-PARAM_ONESHOT_MAX_BYTES, PARAM_NVLS_MIN_WORLD, PARAM_NVLS_CTAS, PARAM_LL_MAX_BYTES = range(4)
+(PARAM_ONESHOT_MAX_BYTES, PARAM_NVLS_MIN_WORLD, PARAM_NVLS_CTAS, PARAM_LL_MAX_BYTES, PARAM_PIPE_MIN_BYTES,
+ PARAM_PIPE_CHUNK_BYTES, PARAM_PIPE_COPY_CTAS, PARAM_PIPE_RED_CTAS, PARAM_PIPE_VARIANT,
+ PARAM_GRAD_LOCAL_UNROLL, PARAM_P2P_BULK_MIN_CHUNK) = range(11)
 # algorithms (b200_algo_t)
-ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_LL = range(5)
+ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_LL, ALGO_PIPE = range(6)
 
 
 class B200Config(ctypes.Structure):

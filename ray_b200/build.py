@@ -22,8 +22,8 @@ INCLUDE = PKG_DIR.parent / "include"
 BUILD_DIR = CSRC / "build"
 LIB_PATH = PKG_DIR / "libb200_collective.so"
 
-SOURCES = ["bootstrap.cu", "allreduce.cu", "reduce_ops.cu", "copy_ops.cu", "p2p.cu", "grad.cu"]
-HEADERS = ["common.cuh", "comm.h", "kernel_utils.cuh", "allreduce_core.cuh"]
+SOURCES = ["bootstrap.cu", "allreduce.cu", "allreduce_pipe.cu", "reduce_ops.cu", "copy_ops.cu", "p2p.cu", "grad.cu"]
+HEADERS = ["common.cuh", "comm.h", "kernel_utils.cuh", "allreduce_core.cuh", "bulk_copy.cuh", "pipe.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -19,6 +19,7 @@
 // CTA b's of all ranks (flags in the signal pad) is the only synchronisation needed:
 // no grid-wide sync, no host involvement.
 #include "allreduce_core.cuh"
+#include "pipe.h"
 
 namespace b200 {
 
@@ -290,6 +291,13 @@ static size_t ll_limit(const b200_comm *c) {
   return lim < kLLMaxPayload ? lim : kLLMaxPayload;
 }
 
+// Measured break-even of the pipelined kernels against the phase-by-phase ones (profiles/r02).
+static size_t pipe_min_bytes(const b200_comm *c) {
+  const long long v = c->params[B200_PARAM_PIPE_MIN_BYTES];
+  if (v >= 0) return size_t(v);
+  return size_t(8) << 20;
+}
+
 static size_t oneshot_limit(const b200_comm *c) {
   static long long env = [] {
     const char *s = getenv("B200_ONESHOT_MAX_BYTES");
@@ -342,12 +350,37 @@ extern "C" int b200_allreduce(b200_comm_t c, const void *in, void *out, size_t c
 
   const char *src = static_cast<const char *>(in);
   char *dst = static_cast<char *>(out);
+
+  // Ordinary (staged) operands from pipe_min_bytes() on: the chunk-pipelined kernels, which overlap
+  // the two staging passes with the NVLink phase (allreduce_pipe.cu).  They move whole 16-byte
+  // units with the bulk-copy engine, so they need aligned operands.
+  int pipe_variant = -1;
+  if (sym_off < 0 && is_aligned16(in) && is_aligned16(out) && (total & 15) == 0 &&
+      (algo == B200_ALGO_PIPE || (algo == B200_ALGO_AUTO && total >= pipe_min_bytes(c)))) {
+    if (c->world == 2) pipe_variant = PIPE_PUSH;
+    else if (c->mc_active && nvls_capable(dtype, op)) pipe_variant = PIPE_NVLS;
+    else if (algo == B200_ALGO_PIPE) pipe_variant = PIPE_PEER;  // AUTO without NVLS keeps the two-shot kernel
+    if (algo == B200_ALGO_PIPE && c->params[B200_PARAM_PIPE_VARIANT] >= 0)
+      pipe_variant = int(c->params[B200_PARAM_PIPE_VARIANT]);
+    if (pipe_variant == PIPE_NVLS && !(c->mc_active && nvls_capable(dtype, op))) pipe_variant = PIPE_PEER;
+  } else if (algo == B200_ALGO_PIPE) {
+    set_error("the pipelined all-reduce needs 16-byte aligned operands outside the symmetric heap "
+              "and a size that is a multiple of 16 bytes");
+    return B200_ERR_UNSUPPORTED;
+  }
+
   // Messages larger than one staging slot are processed slot by slot.
-  const size_t chunk_max = sym_off >= 0 ? total : c->staging_bytes;  // rows <= kMaxTiles is re-checked per launch
+  const size_t chunk_max = sym_off >= 0 ? total : (pipe_variant >= 0 ? pipe_max_bytes(c, pipe_variant) : c->staging_bytes);
   for (size_t done = 0; done < total;) {
     const size_t nbytes = (total - done) < chunk_max ? (total - done) : chunk_max;
+    if (pipe_variant >= 0 && (algo == B200_ALGO_PIPE || nbytes >= pipe_min_bytes(c) || nbytes > c->staging_bytes)) {
+      rc = launch_allreduce_pipe_dyn(c, src + done, dst + done, nbytes, dtype, op, pipe_variant, stream);
+      if (rc) return rc;
+      done += nbytes;
+      continue;
+    }
     int a = algo;
-    if (a == B200_ALGO_AUTO) {
+    if (a == B200_ALGO_AUTO || a == B200_ALGO_PIPE) {
       if (nbytes <= ll_limit(c)) a = B200_ALGO_LL;
       else if (sym_off < 0 && nbytes <= oneshot_limit(c)) a = B200_ALGO_ONESHOT;
       else if (c->mc_active && nvls_capable(dtype, op) && nvls_pays_off(c, nbytes)) a = B200_ALGO_NVLS;

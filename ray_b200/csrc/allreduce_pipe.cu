@@ -1,0 +1,465 @@
+// allreduce_pipe.cu — chunk-pipelined all-reduce for large messages on ORDINARY tensors
+// (operands that do not live in the symmetric heap).
+//
+// The phase-by-phase kernels in allreduce.cu run stage-in, the NVLink phase and stage-out one
+// after the other on the whole grid: two full HBM passes that are never overlapped with the link
+// (round-1 verdict: 0.45-0.63 of the link at 64 MiB).  Here the message is cut into chunks of
+// C bytes and the CTAs of ONE launch take fixed roles that work on different chunks at the same
+// time, synchronised by per-chunk flags in the signal pad (never by a grid-wide or host barrier):
+//
+//   allreduce_pipe_kernel (n >= 3; NVLS when the multicast mapping exists, peer ld/st otherwise)
+//     copy-in  CTAs : user tensor -> own symmetric slot, TMA bulk copies      -> flag0[k][rank]
+//     reduce   CTAs : wait flag0[k][*]; reduce the stripe of chunk k this rank owns
+//                     (multimem.ld_reduce + multimem.st, or n peer loads + n peer stores)
+//                                                                              -> flag1[k][rank]
+//     copy-out CTAs : wait flag1[k][*]; own slot -> user tensor, TMA bulk copies
+//
+//   allreduce_push_kernel (n == 2: one-shot push, the link carries S per direction either way)
+//     push     CTAs : user tensor -> the PEER's slot over NVLink, TMA bulk copies (the stage-in
+//                     pass and the transfer are the same bytes)                -> flag0[k][rank]
+//     reduce   CTAs : wait flag0[k][*]; out = user (op) slot, rank-ascending, straight into the
+//                     caller's tensor -- no stage-out pass at all
+//
+// A copy role is one thread driving the bulk-copy unit (bulk_copy.cuh), so it costs a few CTAs;
+// the reduce roles are ordinary 512-thread CTAs with 16-byte accesses.
+//
+// Flags carry the launch epoch (launch counter * 4 + phase), which only grows, so nothing is ever
+// reset; per-chunk arrival counters live in rank-local memory and are re-zeroed by the last
+// arriver.  Slot rotation and its safety argument are unchanged ("slot rotation"):
+// every rank's completion of a launch depends on every peer having started that launch.
+#include "allreduce_core.cuh"
+#include "bulk_copy.cuh"
+#include "pipe.h"
+
+namespace b200 {
+
+struct PipeArgs {
+  const char *in;
+  char *out;
+  size_t nbytes;         // multiple of 16; in/out 16-byte aligned
+  size_t staging_bytes;
+  size_t chunk_bytes;    // C: multiple of copy_ctas * kBulkTile
+  int copy_ctas;         // CTAs per copy role (power of two)
+};
+
+struct PipeGeom {
+  size_t S, C, K;
+  int G;       // copy CTAs per role
+  uint32_t m;  // tiles per copy CTA per full chunk
+};
+__device__ __forceinline__ PipeGeom make_geom(const PipeArgs &a) {
+  PipeGeom g;
+  g.S = a.nbytes;
+  g.C = a.chunk_bytes;
+  g.K = (g.S + g.C - 1) / g.C;
+  g.G = a.copy_ctas;
+  g.m = uint32_t(g.C / (size_t(g.G) * kBulkTile));
+  return g;
+}
+__device__ __forceinline__ size_t chunk_len(const PipeGeom &g, size_t k) {
+  const size_t lo = k * g.C;
+  return (g.S - lo) < g.C ? (g.S - lo) : g.C;
+}
+// byte offset of the i-th tile of copy CTA j (>= S: past the end)
+__device__ __forceinline__ size_t tile_off(const PipeGeom &g, int j, size_t i) {
+  const size_t k = i / g.m, t = (i % g.m) * size_t(g.G) + size_t(j);
+  return k * g.C + t * kBulkTile;
+}
+__device__ __forceinline__ size_t tiles_of_cta(const PipeGeom &g, int j) {
+  const size_t full = g.S / g.C, rem = g.S - full * g.C;
+  size_t nt = full * g.m;
+  for (uint32_t q = 0; q < g.m; ++q)
+    if ((size_t(q) * g.G + size_t(j)) * kBulkTile < rem) ++nt;
+  return nt;
+}
+// copy CTAs that own at least one tile of chunk k (= arrivals expected on its counter)
+__device__ __forceinline__ uint32_t copy_arrivals(const PipeGeom &g, size_t k) {
+  const size_t tiles = (chunk_len(g, k) + kBulkTile - 1) / kBulkTile;
+  return uint32_t(tiles < size_t(g.G) ? tiles : size_t(g.G));
+}
+
+// One thread: count this CTA's arrival on a chunk; the last arriver re-zeroes the counter and
+// returns true with every CTA's writes ordered before whatever it stores next (system scope:
+// the readers are other GPUs).
+__device__ __forceinline__ bool chunk_arrive(uint32_t *cnt, uint32_t expected) {
+  __threadfence_system();
+  const uint32_t old = atomicAdd(cnt, 1u);
+  if (old + 1u == expected) {
+    *cnt = 0;
+    __threadfence_system();
+    return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void signal_all(const DevComm &c, size_t flag_word, uint32_t value) {
+  for (int i = 0; i < c.world; ++i) {
+    int p = c.rank + i;  // own pad first (local consumers), then walk the peers
+    if (p >= c.world) p -= c.world;
+    st_relaxed_sys(c.sig[p] + flag_word + c.rank, value);
+  }
+}
+// All threads: wait until every rank's flag of chunk k reached `value`.
+__device__ __forceinline__ bool cta_wait_chunk(const DevComm &c, size_t flag_base, size_t k, uint32_t value) {
+  __shared__ int ok_flag;
+  if (threadIdx.x == 0) ok_flag = 1;
+  __syncthreads();
+  if (threadIdx.x < c.world) {
+    if (!wait_flag_ge(c, c.sig[c.rank] + flag_base + k * kMaxRanks + threadIdx.x, value)) ok_flag = 0;
+  }
+  __syncthreads();
+  return ok_flag != 0;
+}
+// One thread (the bulk-copy driver): same test, optionally non-blocking.
+__device__ __forceinline__ int thread_wait_chunk(const DevComm &c, size_t flag_base, size_t k, uint32_t value,
+                                                 bool block) {
+  const uint32_t *f = c.sig[c.rank] + flag_base + k * kMaxRanks;
+  for (int p = 0; p < c.world; ++p) {
+    if (block) {
+      if (!wait_flag_ge(c, f + p, value)) return -1;
+    } else if (int32_t(ld_acquire_sys(f + p) - value) < 0) {
+      return 0;
+    }
+  }
+  return 1;
+}
+
+constexpr int kItemUnroll = 4;
+constexpr size_t kItemUnits = size_t(kThreads) * kItemUnroll;  // 16-byte units per reduce work item
+
+// ---------------------------------------------------------------------------
+// n >= 3: copy-in | reduce (NVLS or peer ld/st) | copy-out
+// ---------------------------------------------------------------------------
+template <typename T, int OP, bool NVLS>
+__global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, PipeArgs a) {
+  extern __shared__ __align__(128) char dyn_smem[];
+  using Tr = Traits<T>;
+  const uint32_t launch = c.st->launch_ctr;
+  const uint32_t ep = launch * 4u;
+  const size_t off = staging_slot_offset(launch, a.staging_bytes);
+  const PipeGeom g = make_geom(a);
+  const int n = c.world, r = c.rank;
+  const int G = g.G, Gr = int(gridDim.x) - 2 * G;
+  const int b = blockIdx.x;
+
+  if (b < G) {
+    // ---- copy-in -------------------------------------------------------------------------
+    const BulkRing ring = bulk_ring_init(dyn_smem);
+    if (threadIdx.x == 0) {
+      const int j = b;
+      const size_t nt = tiles_of_cta(g, j);
+      char *slot = c.data[r] + off;
+      bulk_copy_run(
+          ring, nt, [&](size_t i) {
+            const size_t o = tile_off(g, j, i);
+            return BulkTileDesc{a.in + o, uint32_t((g.S - o) < size_t(kBulkTile) ? (g.S - o) : size_t(kBulkTile))};
+          },
+          [&](size_t i, uint32_t smem, uint32_t bytes) { bulk_s2g(slot + tile_off(g, j, i), smem, bytes); },
+          [&](size_t, bool) { return 1; },
+          [&](size_t i) {
+            if ((i % g.m) == g.m - 1 || i + 1 == nt) {  // this CTA's last tile of chunk k
+              const size_t k = i / g.m;
+              fence_proxy_async();
+              if (chunk_arrive(&c.st->pipe_cnt[0][k], copy_arrivals(g, k)))
+                signal_all(c, kSigPipe0 + k * kMaxRanks, ep + 1);
+            }
+          });
+    }
+  } else if (b < G + Gr) {
+    // ---- reduce ------------------------------------------------------------------------------
+    const int me = b - G;
+    size_t item_base = 0;  // global index of chunk k's first work item
+    for (size_t k = 0; k < g.K; ++k) {
+      const size_t cu = chunk_len(g, k) >> 4;           // units in this chunk
+      const size_t lo = cu * size_t(r) / size_t(n);     // this rank's stripe
+      const size_t hi = cu * size_t(r + 1) / size_t(n);
+      const size_t items = (hi - lo + kItemUnits - 1) / kItemUnits;
+      const size_t nitems = items ? items : 1;          // an empty stripe still publishes
+      size_t it = (size_t(me) + size_t(Gr) - item_base % size_t(Gr)) % size_t(Gr);
+      item_base += nitems;
+      if (it >= nitems) continue;
+      if (!cta_wait_chunk(c, kSigPipe0, k, ep + 1)) break;
+      const size_t cbase = off + k * g.C;
+      for (; it < nitems; it += size_t(Gr)) {
+        const size_t u0 = lo + it * kItemUnits + threadIdx.x;
+        if (NVLS) {
+          char *mc = c.mc_data + cbase;
+          uint4 v[kItemUnroll];
+#pragma unroll
+          for (int q = 0; q < kItemUnroll; ++q) {
+            const size_t u = u0 + size_t(q) * kThreads;
+            if (u < hi) v[q] = Multimem<T>::ld_reduce_sum(mc + (u << 4));
+          }
+#pragma unroll
+          for (int q = 0; q < kItemUnroll; ++q) {
+            const size_t u = u0 + size_t(q) * kThreads;
+            if (u < hi) {
+              if (OP == B200_AVG) {
+                typename Tr::Acc acc = Tr::unpack(v[q]);
+                Tr::average(acc, n);
+                v[q] = Tr::pack(acc);
+              }
+              multimem_st(mc + (u << 4), v[q]);
+            }
+          }
+        } else {
+#pragma unroll 2
+          for (int q = 0; q < kItemUnroll; ++q) {
+            const size_t u = u0 + size_t(q) * kThreads;
+            if (u < hi) {
+              uint4 v[kMaxRanks];
+#pragma unroll
+              for (int p = 0; p < kMaxRanks; ++p)
+                if (p < n) v[p] = ld_peer(c.data[p] + cbase + (u << 4));
+              typename Tr::Acc acc = Tr::unpack(v[0]);
+#pragma unroll
+              for (int p = 1; p < kMaxRanks; ++p)
+                if (p < n) Tr::template reduce<OP>(acc, Tr::unpack(v[p]));  // rank-ascending
+              if (OP == B200_AVG) Tr::average(acc, n);
+              const uint4 res = Tr::pack(acc);
+#pragma unroll
+              for (int i = 0; i < kMaxRanks; ++i) {
+                if (i < n) {
+                  int p = r + i;
+                  if (p >= n) p -= n;
+                  st_vec(c.data[p] + cbase + (u << 4), res);
+                }
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && chunk_arrive(&c.st->pipe_cnt[1][k], uint32_t(nitems)))
+          signal_all(c, kSigPipe1 + k * kMaxRanks, ep + 2);
+      }
+    }
+  } else {
+    // ---- copy-out ------------------------------------------------------------------------
+    const BulkRing ring = bulk_ring_init(dyn_smem);
+    if (threadIdx.x == 0) {
+      const int j = b - G - Gr;
+      const size_t nt = tiles_of_cta(g, j);
+      const char *slot = c.data[r] + off;
+      size_t ready = 0;  // chunks [0, ready) are published by every rank
+      bulk_copy_run(
+          ring, nt, [&](size_t i) {
+            const size_t o = tile_off(g, j, i);
+            return BulkTileDesc{slot + o, uint32_t((g.S - o) < size_t(kBulkTile) ? (g.S - o) : size_t(kBulkTile))};
+          },
+          [&](size_t i, uint32_t smem, uint32_t bytes) { bulk_s2g(a.out + tile_off(g, j, i), smem, bytes); },
+          [&](size_t i, bool block) {
+            const size_t k = i / g.m;
+            if (k < ready) return 1;
+            const int st = thread_wait_chunk(c, kSigPipe1, k, ep + 2, block);
+            if (st == 1) {
+              ready = k + 1;
+              fence_proxy_async();  // peers' stores (generic proxy) before our bulk reads (async proxy)
+            }
+            return st;
+          },
+          [&](size_t) {});
+    }
+  }
+  finish_launch(c);
+}
+
+// ---------------------------------------------------------------------------
+// one-shot push (selected for n == 2; correct for any n with (n-1)*S <= slot)
+// ---------------------------------------------------------------------------
+template <typename T, int OP, int UNR, int NW>  // NW: compile-time bound on the world size
+__device__ __forceinline__ void push_reduce_item(const DevComm &c, const PipeArgs &a, size_t sub, size_t off,
+                                                 size_t ubase, size_t u0, size_t uend) {
+  using Tr = Traits<T>;
+  const int n = c.world, r = c.rank;
+  const char *slot = c.data[r] + off;
+  uint4 v[UNR][NW];
+#pragma unroll
+  for (int q = 0; q < UNR; ++q) {
+    const size_t u = u0 + size_t(q) * kThreads;
+    if (u < uend) {
+      const size_t byte = (ubase + u) << 4;
+#pragma unroll
+      for (int p = 0; p < NW; ++p) {
+        if (p < n) {
+          if (p == r) v[q][p] = ld_stream(a.in + byte);
+          else v[q][p] = ld_peer(slot + size_t(p < r ? p : p - 1) * sub + byte);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < UNR; ++q) {
+    const size_t u = u0 + size_t(q) * kThreads;
+    if (u < uend) {
+      typename Tr::Acc acc = Tr::unpack(v[q][0]);
+#pragma unroll
+      for (int p = 1; p < NW; ++p)
+        if (p < n) Tr::template reduce<OP>(acc, Tr::unpack(v[q][p]));  // rank-ascending
+      if (OP == B200_AVG) Tr::average(acc, n);
+      st_vec(a.out + ((ubase + u) << 4), Tr::pack(acc));
+    }
+  }
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(kThreads, 1) allreduce_push_kernel(DevComm c, PipeArgs a) {
+  extern __shared__ __align__(128) char dyn_smem[];
+  const uint32_t launch = c.st->launch_ctr;
+  const uint32_t ep = launch * 4u;
+  const size_t off = staging_slot_offset(launch, a.staging_bytes);
+  const PipeGeom g = make_geom(a);
+  const int n = c.world, r = c.rank;
+  const int G = g.G, Gr = int(gridDim.x) - G;
+  const int b = blockIdx.x;
+  const size_t sub = g.S;  // bytes per source sub-slot (S is a multiple of 16)
+
+  if (b < G) {
+    // ---- push: my tensor into every peer's slot, sub-slot "me" ------------------------------
+    const BulkRing ring = bulk_ring_init(dyn_smem);
+    if (threadIdx.x == 0) {
+      const int j = b;
+      const size_t nt = tiles_of_cta(g, j);
+      bulk_copy_run(
+          ring, nt, [&](size_t i) {
+            const size_t o = tile_off(g, j, i);
+            return BulkTileDesc{a.in + o, uint32_t((g.S - o) < size_t(kBulkTile) ? (g.S - o) : size_t(kBulkTile))};
+          },
+          [&](size_t i, uint32_t smem, uint32_t bytes) {
+            const size_t o = tile_off(g, j, i);
+            for (int q = 1; q < n; ++q) {
+              int p = r + q;
+              if (p >= n) p -= n;
+              bulk_s2g(c.data[p] + off + size_t(r < p ? r : r - 1) * sub + o, smem, bytes);
+            }
+          },
+          [&](size_t, bool) { return 1; },
+          [&](size_t i) {
+            if ((i % g.m) == g.m - 1 || i + 1 == nt) {
+              const size_t k = i / g.m;
+              fence_proxy_async();
+              if (chunk_arrive(&c.st->pipe_cnt[0][k], copy_arrivals(g, k)))
+                signal_all(c, kSigPipe0 + k * kMaxRanks, ep + 1);
+            }
+          });
+    }
+  } else {
+    // ---- reduce: own tensor (op) what the peers pushed, straight into the caller's tensor ---
+    const int me = b - G;
+    size_t item_base = 0;
+    for (size_t k = 0; k < g.K; ++k) {
+      const size_t cu = chunk_len(g, k) >> 4;
+      const size_t nitems = (cu + kItemUnits - 1) / kItemUnits;
+      size_t it = (size_t(me) + size_t(Gr) - item_base % size_t(Gr)) % size_t(Gr);
+      item_base += nitems;
+      if (it >= nitems) continue;
+      // flag0[k][p] for p != r: p's chunk has landed here; p == r: the local push CTAs are done
+      // READING chunk k of the caller's tensor, so it may be overwritten in place.
+      if (!cta_wait_chunk(c, kSigPipe0, k, ep + 1)) break;
+      const size_t ubase = (k * g.C) >> 4;
+      for (; it < nitems; it += size_t(Gr)) {
+        const size_t u0 = it * kItemUnits + threadIdx.x;
+        if (n == 2) {
+          push_reduce_item<T, OP, 4, 2>(c, a, sub, off, ubase, u0, cu);
+        } else {
+#pragma unroll 1
+          for (int q = 0; q < kItemUnroll; ++q)
+            push_reduce_item<T, OP, 1, kMaxRanks>(c, a, sub, off, ubase, u0 + size_t(q) * kThreads, cu);
+        }
+      }
+    }
+  }
+  finish_launch(c);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int pow2_floor(int x) {
+  int p = 1;
+  while (p * 2 <= x) p *= 2;
+  return p;
+}
+
+// Opt the kernel into kBulkSmemBytes of dynamic shared memory, once per (device, kernel): the
+// attribute call is kept out of the steady-state launch path (and out of stream capture).
+int set_dyn_smem(int device, const void *fn) {
+  static std::mutex mu;
+  static std::vector<std::pair<int, const void *>> seen;
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto &e : seen)
+    if (e.first == device && e.second == fn) return B200_OK;
+  B200_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBulkSmemBytes)));
+  seen.emplace_back(device, fn);
+  return B200_OK;
+}
+
+size_t pipe_max_bytes(const b200_comm *c, int variant) {
+  const size_t C = pipe_chunk_bytes(c);
+  size_t cap = c->staging_bytes;
+  if (variant == PIPE_PUSH) cap = c->staging_bytes / size_t(c->world - 1);
+  const size_t by_chunks = size_t(kMaxPipeChunks) * C;
+  cap = cap < by_chunks ? cap : by_chunks;
+  return cap / C * C;  // whole chunks, so a split message continues on a chunk boundary
+}
+
+size_t pipe_chunk_bytes(const b200_comm *c) {
+  const long long v = c->params[B200_PARAM_PIPE_CHUNK_BYTES];
+  size_t C = v > 0 ? size_t(v) : (size_t(1) << 20);
+  const size_t quantum = size_t(64) * kBulkTile;  // any power-of-two copy-CTA count up to 64 divides it
+  return round_up(C, quantum);
+}
+
+template <typename T, int OP>
+int launch_allreduce_pipe(b200_comm *c, const char *in, char *out, size_t nbytes, int variant,
+                          cudaStream_t stream) {
+  PipeArgs a{in, out, nbytes, c->staging_bytes, pipe_chunk_bytes(c), 0};
+  const long long pc = c->params[B200_PARAM_PIPE_COPY_CTAS];
+  const long long pr = c->params[B200_PARAM_PIPE_RED_CTAS];
+  int G = pc > 0 ? int(pc) : (variant == PIPE_PUSH ? 16 : 8);
+  int Gr = pr > 0 ? int(pr) : 48;
+  const int roles = variant == PIPE_PUSH ? 1 : 2;
+  int cap = c->forced_blocks > 0 ? c->forced_blocks : c->sm_count;
+  if (roles * G + Gr > cap) {  // shared-GPU harness / small parts: shrink, keep at least one reducer
+    while (G > 1 && roles * G + 1 > cap / 2) G /= 2;
+    Gr = cap - roles * G;
+    if (Gr < 1) {
+      set_error("pipelined all-reduce needs at least %d CTAs (have %d)", roles + 1, cap);
+      return B200_ERR_UNSUPPORTED;
+    }
+  }
+  G = pow2_floor(G > 64 ? 64 : G);
+  a.copy_ctas = G;
+  const int grid = roles * G + Gr;
+  DevComm dc = c->dev();
+  int rc = B200_OK;
+  if (variant == PIPE_PUSH) {
+    auto k = allreduce_push_kernel<T, OP>;
+    if ((rc = set_dyn_smem(c->device, reinterpret_cast<const void *>(k)))) return rc;
+    k<<<grid, kThreads, kBulkSmemBytes, stream>>>(dc, a);
+  } else if (variant == PIPE_NVLS) {
+    if constexpr (Multimem<T>::kSum && (OP == B200_SUM || OP == B200_AVG)) {
+      auto k = allreduce_pipe_kernel<T, OP, true>;
+      if ((rc = set_dyn_smem(c->device, reinterpret_cast<const void *>(k)))) return rc;
+      k<<<grid, kThreads, kBulkSmemBytes, stream>>>(dc, a);
+    } else {
+      set_error("NVLS all-reduce supports SUM/AVG on f32/f16/bf16 only");
+      return B200_ERR_UNSUPPORTED;
+    }
+  } else {
+    auto k = allreduce_pipe_kernel<T, OP, false>;
+    if ((rc = set_dyn_smem(c->device, reinterpret_cast<const void *>(k)))) return rc;
+    k<<<grid, kThreads, kBulkSmemBytes, stream>>>(dc, a);
+  }
+  B200_LAUNCH_CHECK(c);
+  return B200_OK;
+}
+
+int launch_allreduce_pipe_dyn(b200_comm *c, const char *in, char *out, size_t nbytes, int dtype, int op,
+                              int variant, cudaStream_t stream) {
+  int rc = B200_OK;
+  B200_DISPATCH_DTYPE(dtype, T, B200_DISPATCH_OP(op, OP, {
+                        rc = launch_allreduce_pipe<T, OP>(c, in, out, nbytes, variant, stream);
+                      }));
+  return rc;
+}
+
+}  // namespace b200

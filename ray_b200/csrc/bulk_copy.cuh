@@ -1,0 +1,146 @@
+// bulk_copy.cuh — TMA bulk-copy engine (cp.async.bulk, SASS UBLKCP) driven by ONE thread of a CTA.
+//
+// The copy phases of the collectives (user tensor -> symmetric slot, slot -> user tensor, user
+// tensor -> a peer's slot or inbox over NVLink) are pure byte movement.  Done with ld/st they need
+// tens of CTAs x 512 threads to keep enough bytes in flight; done with the bulk-copy unit a single
+// thread keeps NST x TILE bytes in flight per CTA:
+//
+//     global --cp.async.bulk + mbarrier complete_tx--> shared ring --cp.async.bulk.bulk_group--> global
+//
+// so a copy role costs a handful of CTAs (one busy thread each) instead of the whole GPU, and the
+// SMs stay available to the kernels the collective overlaps with (DDP backward).
+//
+// Requirements: source, destination and length of every tile are multiples of 16 bytes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kBulkTile = 16 << 10;  // bytes per tile
+constexpr int kBulkStages = 12;      // ring depth (12 x 16 KiB = 192 KiB of shared memory)
+constexpr int kBulkLookahead = 4;    // loads issued ahead of the store cursor
+constexpr int kBulkPending = kBulkStages - kBulkLookahead - 1;  // store groups allowed in flight
+constexpr size_t kBulkSmemBytes = size_t(kBulkStages) * kBulkTile + 16 * kBulkStages;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// shared -> global (local HBM or a peer's memory over NVLink), tracked by bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() {  // all but the N most recent groups have COMPLETED (writes done)
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// orders async-proxy accesses (bulk copies) against generic-proxy accesses (ld/st, flags)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+struct BulkTileDesc {
+  const char *src;
+  uint32_t bytes;
+};
+
+// Shared-memory carve-up of a copy CTA (dynamic shared memory, kBulkSmemBytes).
+struct BulkRing {
+  uint32_t tiles;  // shared address of tile 0
+  uint32_t bars;   // shared address of mbarrier 0
+};
+
+// Every thread of the CTA calls this once before the copy role starts.
+__device__ __forceinline__ BulkRing bulk_ring_init(char *dyn_smem) {
+  BulkRing r;
+  r.tiles = smem_u32(dyn_smem);
+  r.bars = r.tiles + kBulkStages * kBulkTile;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBulkStages; ++s) mbar_init(r.bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  return r;
+}
+
+// Runs the whole tile sequence of one copy role.  Called by exactly one thread.
+//   tile(i)        -> source and length of the i-th tile (pure function of i; called once when the
+//                     load is issued and once when the store is issued)
+//   emit(i, smem, bytes) -> issues the bulk store(s) of tile i from shared address `smem`
+//                     (bulk_s2g; several when the tile goes to several peers)
+//   gate(i, block) -> asked before the LOAD of tile i is issued: 1 = source valid / destination
+//                     free, 0 = not yet (only when !block), -1 = abandon (abort / watchdog).
+//                     The engine first asks without blocking; if the answer is 0 and nothing else
+//                     can make progress it drains its pending stores (so every done() it owes has
+//                     been delivered -- a peer may be waiting for exactly that) and asks again with
+//                     block = true.
+//   done(i)        -> called, in order, once the STORE of tile i has completed
+// Returns false when abandoned.
+template <typename TileFn, typename EmitFn, typename GateFn, typename DoneFn>
+__device__ __forceinline__ bool bulk_copy_run(const BulkRing &ring, size_t ntiles, TileFn tile, EmitFn emit,
+                                              GateFn gate, DoneFn done) {
+  size_t load_i = 0, store_j = 0, completed = 0;
+  bool ok = true;
+  while (store_j < ntiles) {
+    while (load_i < ntiles && load_i - store_j < size_t(kBulkLookahead) && load_i - completed < size_t(kBulkStages)) {
+      const int g = gate(load_i, false);
+      if (g < 0) ok = false;
+      if (g <= 0) break;
+      const int s = int(load_i % kBulkStages);
+      const BulkTileDesc d = tile(load_i);
+      mbar_expect_tx(ring.bars + 8 * s, d.bytes);
+      bulk_g2s(ring.tiles + uint32_t(s) * kBulkTile, d.src, d.bytes, ring.bars + 8 * s);
+      ++load_i;
+    }
+    if (store_j < load_i) {
+      const int s = int(store_j % kBulkStages);
+      const uint32_t parity = uint32_t(store_j / kBulkStages) & 1u;
+      while (!mbar_try_wait(ring.bars + 8 * s, parity)) {
+      }
+      const BulkTileDesc d = tile(store_j);
+      emit(store_j, ring.tiles + uint32_t(s) * kBulkTile, d.bytes);
+      bulk_commit();
+      ++store_j;
+      bulk_wait<kBulkPending>();
+      for (; completed + kBulkPending < store_j; ++completed) done(completed);
+    } else {
+      // nothing in flight towards shared memory and the next source is not ready
+      bulk_wait<0>();
+      for (; completed < store_j; ++completed) done(completed);
+      if (!ok) break;
+      if (gate(load_i, true) < 0) {
+        ok = false;
+        break;
+      }
+    }
+    if (!ok && store_j == load_i) break;
+  }
+  bulk_wait<0>();
+  for (; completed < store_j; ++completed) done(completed);
+  return ok;
+}
+
+}  // namespace b200

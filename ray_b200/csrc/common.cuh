@@ -9,6 +9,7 @@
 //                    coll flags  [MAX_BLOCKS][MAX_RANKS]
 //                    p2p ready   [MAX_RANKS src][P2P_RINGS][P2P_SLOTS]
 //                    p2p ack     [MAX_RANKS dst][P2P_RINGS]
+//                    pipe flags  [2 kinds][MAX_PIPE_CHUNKS][MAX_RANKS]
 //   region "inbox" : [MAX_RANKS src] x inbox_bytes point-to-point landing area
 //   region "ll"    : [2][MAX_RANKS src][128 KiB] flag-in-data slots of the low-latency all-reduce
 //
@@ -27,14 +28,19 @@ namespace b200 {
 constexpr int kMaxRanks = B200_MAX_RANKS;
 constexpr int kMaxBlocks = 512;   // upper bound on collective grid size (flag rows)
 constexpr int kThreads = 512;     // CTA size of every collective kernel
-constexpr int kP2PRings = 64;     // independent sub-rings per ordered pair (one per CTA)
-constexpr int kP2PSlots = 4;      // chunks in flight per sub-ring
+constexpr int kP2PRings = 16;     // independent sub-rings per ordered pair (one per CTA)
+constexpr int kP2PSlots = 8;      // chunks in flight per sub-ring
 
 // signal pad offsets, in u32 words
 constexpr size_t kSigCollFlags = 0;
 constexpr size_t kSigP2PReady = kSigCollFlags + size_t(kMaxBlocks) * kMaxRanks;
 constexpr size_t kSigP2PAck = kSigP2PReady + size_t(kMaxRanks) * kP2PRings * kP2PSlots;
-constexpr size_t kSigWords = kSigP2PAck + size_t(kMaxRanks) * kP2PRings;
+// pipelined all-reduce: per-chunk flags, two kinds (0: "rank p's copy of chunk k is in place",
+// 1: "rank p published its stripe of chunk k"), each [kMaxPipeChunks][kMaxRanks]
+constexpr int kMaxPipeChunks = 512;
+constexpr size_t kSigPipe0 = kSigP2PAck + size_t(kMaxRanks) * kP2PRings;
+constexpr size_t kSigPipe1 = kSigPipe0 + size_t(kMaxPipeChunks) * kMaxRanks;
+constexpr size_t kSigWords = kSigPipe1 + size_t(kMaxPipeChunks) * kMaxRanks;
 
 // Low-latency (LL) region: [2 parities][kMaxRanks sources][kLLSlotBytes]; payload and flag share
 // each 8-byte word pair, so a message needs no separate barrier.
@@ -50,6 +56,7 @@ struct LocalState {
   uint32_t pad;
   uint32_t send_seq[kMaxRanks][kP2PRings];  // next chunk sequence to peer, per ring
   uint32_t recv_seq[kMaxRanks][kP2PRings];  // next chunk sequence from peer, per ring
+  uint32_t pipe_cnt[2][kMaxPipeChunks];     // per-chunk arrival counters of the pipelined kernels
 };
 
 // Passed by value to every kernel.

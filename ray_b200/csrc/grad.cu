@@ -139,29 +139,35 @@ __global__ void __launch_bounds__(kThreads, 1) grad_allreduce_kernel(DevComm c, 
 }
 
 // world == 1: the same arithmetic without any peer (scale, round-trip through the wire type).
-// Pure HBM streaming (8 B per element): 4 units per thread with all loads issued before the
-// first store, 256-thread CTAs, a few CTAs per SM.
+// Pure HBM streaming (8 B per element).  One-shot grid: every thread owns UNR wire units (all
+// loads issued before the first store) and the hardware CTA scheduler does the load balancing --
+// no flag rows are involved, so the grid is NOT clamped to kMaxBlocks (round-1 ran this kernel
+// at 43 % occupancy because of that clamp).
 constexpr int kLocalThreads = 256;
-constexpr int kLocalUnroll = 4;
-template <typename W>
+template <typename W, int UNR>
 __global__ void __launch_bounds__(kLocalThreads) grad_local_kernel(GradArgs a) {
   constexpr int E = Wire<W>::kElems;
   const size_t U = (a.count + E - 1) / E;
   const bool al = is_aligned16(a.grad);
-  const size_t stride = size_t(gridDim.x) * kLocalThreads * kLocalUnroll;
-  for (size_t u0 = size_t(blockIdx.x) * kLocalThreads * kLocalUnroll + threadIdx.x; u0 < U; u0 += stride) {
-    uint4 w[kLocalUnroll];
+  const size_t u0 = size_t(blockIdx.x) * kLocalThreads * UNR + threadIdx.x;
+  uint4 w[UNR];
 #pragma unroll
-    for (int k = 0; k < kLocalUnroll; ++k) {
-      const size_t u = u0 + size_t(k) * kLocalThreads;
-      if (u < U) w[k] = load_grad_unit<W>(a.grad, u, a.count, a.scale, al);
-    }
-#pragma unroll
-    for (int k = 0; k < kLocalUnroll; ++k) {
-      const size_t u = u0 + size_t(k) * kLocalThreads;
-      if (u < U) store_grad_unit<W>(a.grad, u, a.count, al, w[k]);
-    }
+  for (int k = 0; k < UNR; ++k) {
+    const size_t u = u0 + size_t(k) * kLocalThreads;
+    if (u < U) w[k] = load_grad_unit<W>(a.grad, u, a.count, a.scale, al);
   }
+#pragma unroll
+  for (int k = 0; k < UNR; ++k) {
+    const size_t u = u0 + size_t(k) * kLocalThreads;
+    if (u < U) store_grad_unit<W>(a.grad, u, a.count, al, w[k]);
+  }
+}
+
+template <typename W, int UNR>
+static void launch_grad_local(const GradArgs &a, size_t U, cudaStream_t stream) {
+  const size_t per_cta = size_t(kLocalThreads) * UNR;
+  const size_t g = (U + per_cta - 1) / per_cta;
+  grad_local_kernel<W, UNR><<<unsigned(g), kLocalThreads, 0, stream>>>(a);
 }
 
 template <typename W>
@@ -169,9 +175,14 @@ static int launch_grad(b200_comm *c, GradArgs a, cudaStream_t stream) {
   constexpr int E = Wire<W>::kElems;
   const size_t U = (a.count + E - 1) / E;
   if (c->world == 1) {
-    const size_t per_cta = size_t(kLocalThreads) * kLocalUnroll;
-    int g = pick_blocks(c, (U + per_cta - 1) / per_cta, 8 * c->sm_count);
-    grad_local_kernel<W><<<g, kLocalThreads, 0, stream>>>(a);
+    // units per thread: tuning knob, default measured on B200 (profiles/r02/grad_local_sweep.txt)
+    const long long unr = c->params[B200_PARAM_GRAD_LOCAL_UNROLL];
+    switch (unr > 0 ? int(unr) : 2) {
+      case 1: launch_grad_local<W, 1>(a, U, stream); break;
+      case 4: launch_grad_local<W, 4>(a, U, stream); break;
+      case 8: launch_grad_local<W, 8>(a, U, stream); break;
+      default: launch_grad_local<W, 2>(a, U, stream); break;
+    }
     B200_LAUNCH_CHECK(c);
     return B200_OK;
   }

@@ -15,7 +15,18 @@
 // Sequence numbers persist in rank-local device memory, so messages of any size
 // interleave correctly and a send completes without the receiver having been
 // launched as long as the message fits the ring (eager protocol).
+//
+// Two copy mechanisms share this ONE protocol (each side picks its own, per launch):
+//   p2p_kernel      : 512 threads x 16-byte ld/st -- small, unaligned or ragged messages
+//   p2p_bulk_kernel : one thread per CTA drives the TMA bulk-copy unit (cp.async.bulk, SASS
+//                     UBLKCP): user tensor -> shared ring -> peer inbox on the sender, inbox ->
+//                     shared ring -> user tensor on the receiver.  A CTA keeps 192 KiB in flight,
+//                     so <= 16 CTAs fill the link where the ld/st kernel needed 64; a second
+//                     thread publishes the ready / ack flags so the copy thread never waits for a
+//                     system-scope fence.
+#include "bulk_copy.cuh"
 #include "kernel_utils.cuh"
+#include "pipe.h"
 
 namespace b200 {
 
@@ -76,7 +87,8 @@ __global__ void __launch_bounds__(kThreads, 1) p2p_kernel(DevComm c, P2PArgs a) 
     if (SEND) {
       // slot free once the receiver consumed chunk (seq - kP2PSlots)
       if (!cta_wait_flag(c, ack, seq + 1u - kP2PSlots)) break;
-      // 8 x 16 B per thread in flight: one CTA sustains ~20 GB/s, so 64 rings are needed to saturate the link
+      // 8 x 16 B per thread in flight (one CTA sustains ~20 GB/s this way; large aligned messages
+      // take p2p_bulk_kernel instead)
       for (size_t u0 = threadIdx.x; u0 < U; u0 += size_t(kThreads) * 8) {
         uint4 v[8];
 #pragma unroll
@@ -116,6 +128,109 @@ __global__ void __launch_bounds__(kThreads, 1) p2p_kernel(DevComm c, P2PArgs a) 
   if (threadIdx.x == 0) *seq_word = seq;
 }
 
+// ---------------------------------------------------------------------------
+// bulk-copy variant: same rings, same flags, same sequence numbers
+// ---------------------------------------------------------------------------
+template <bool SEND>
+__global__ void __launch_bounds__(kThreads, 1) p2p_bulk_kernel(DevComm c, P2PArgs a) {
+  extern __shared__ __align__(128) char dyn_smem[];
+  __shared__ volatile uint32_t mailbox;  // chunks of this CTA whose bytes have all been moved
+  __shared__ volatile int stop;
+  const int me = c.rank, peer = a.peer;
+  const int b = blockIdx.x, G = gridDim.x;
+  const size_t ring_bytes = c.inbox_bytes / kP2PRings;
+  const size_t slot_bytes = ring_bytes / kP2PSlots;
+  const size_t chunk = a.chunk;
+  const size_t nchunks = (a.nbytes + chunk - 1) / chunk;
+  const size_t nq = nchunks > size_t(b) ? (nchunks - 1 - size_t(b)) / size_t(G) + 1 : 0;  // chunks of this CTA
+
+  uint32_t *seq_word = SEND ? &c.st->send_seq[peer][b] : &c.st->recv_seq[peer][b];
+  const uint32_t seq0 = *seq_word;
+  char *ring = (SEND ? c.inbox[peer] + size_t(me) * c.inbox_bytes : c.inbox[me] + size_t(peer) * c.inbox_bytes) +
+               size_t(b) * ring_bytes;
+  uint32_t *ready = (SEND ? c.sig[peer] + kSigP2PReady + (size_t(me) * kP2PRings + b) * kP2PSlots
+                          : c.sig[me] + kSigP2PReady + (size_t(peer) * kP2PRings + b) * kP2PSlots);
+  uint32_t *ack = (SEND ? c.sig[me] + kSigP2PAck + size_t(peer) * kP2PRings + b
+                        : c.sig[peer] + kSigP2PAck + size_t(me) * kP2PRings + b);
+  if (threadIdx.x == 0) {
+    mailbox = 0;
+    stop = 0;
+  }
+  const BulkRing br = bulk_ring_init(dyn_smem);  // contains the __syncthreads
+
+  const size_t tpc = (chunk + kBulkTile - 1) / kBulkTile;  // tiles of a full chunk
+  auto chunk_lo = [&](size_t q) { return (size_t(b) + q * size_t(G)) * chunk; };
+  auto chunk_len = [&](size_t q) {
+    const size_t lo = chunk_lo(q);
+    return (a.nbytes - lo) < chunk ? (a.nbytes - lo) : chunk;
+  };
+  if (threadIdx.x == 0 && nq > 0) {
+    // ---- copy thread ---------------------------------------------------------------------
+    const size_t last_tiles = (chunk_len(nq - 1) + kBulkTile - 1) / kBulkTile;
+    const size_t nt = (nq - 1) * tpc + last_tiles;
+    size_t gated = 0;  // chunks [0, gated) passed their gate
+    auto slot_of = [&](size_t q) { return ring + size_t((seq0 + uint32_t(q)) % kP2PSlots) * slot_bytes; };
+    const bool ok = bulk_copy_run(
+        br, nt,
+        [&](size_t i) {
+          const size_t q = i / tpc, t = i % tpc;
+          const size_t len = chunk_len(q), o = t * kBulkTile;
+          const uint32_t bytes = uint32_t((len - o) < size_t(kBulkTile) ? (len - o) : size_t(kBulkTile));
+          return BulkTileDesc{SEND ? a.buf + chunk_lo(q) + o : slot_of(q) + o, bytes};
+        },
+        [&](size_t i, uint32_t smem, uint32_t bytes) {
+          const size_t q = i / tpc, o = (i % tpc) * kBulkTile;
+          bulk_s2g(SEND ? slot_of(q) + o : a.buf + chunk_lo(q) + o, smem, bytes);
+        },
+        [&](size_t i, bool block) {
+          const size_t q = i / tpc;
+          if (q < gated) return 1;
+          const uint32_t seq = seq0 + uint32_t(q);
+          // sender: the slot was consumed (ack in MY pad); receiver: the chunk landed (ready in MY pad)
+          const uint32_t *flag = SEND ? ack : ready + seq % kP2PSlots;
+          const uint32_t target = SEND ? seq + 1u - kP2PSlots : seq + 1u;
+          if (block) {
+            if (!wait_flag_ge(c, flag, target)) return -1;
+          } else if (int32_t(ld_acquire_sys(flag) - target) < 0) {
+            return 0;
+          }
+          if (!SEND) fence_proxy_async();  // the peer's stores before our bulk reads
+          gated = q + 1;
+          return 1;
+        },
+        [&](size_t i) {
+          const size_t q = i / tpc, t = i % tpc;
+          const size_t tiles = (chunk_len(q) + kBulkTile - 1) / kBulkTile;
+          if (t + 1 == tiles) {
+            __threadfence_block();
+            mailbox = uint32_t(q + 1);
+          }
+        });
+    if (!ok) stop = 1;
+  } else if (threadIdx.x == 32 && nq > 0) {
+    // ---- flag thread: publishes "ready" (sender) / "ack" (receiver) for completed chunks ------
+    uint32_t published = 0;
+    while (published < nq) {
+      const uint32_t avail = mailbox;
+      if (avail == published) {
+        if (stop) break;
+        __nanosleep(64);
+        continue;
+      }
+      __threadfence_block();
+      fence_proxy_async();
+      __threadfence_system();
+      for (; published < avail; ++published) {
+        const uint32_t seq = seq0 + published;
+        if (SEND) st_relaxed_sys(ready + seq % kP2PSlots, seq + 1u);
+        else st_relaxed_sys(ack, seq + 1u);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *seq_word = seq0 + uint32_t(stop ? mailbox : nq);
+}
+
 static int p2p_common(b200_comm *c, void *buf, size_t nbytes, int peer, cudaStream_t stream, bool send) {
   int rc = check_usable(c);
   if (rc) return rc;
@@ -138,8 +253,21 @@ static int p2p_common(b200_comm *c, void *buf, size_t nbytes, int peer, cudaStre
   // Grid is a pure function of the message size so both sides pair CTA b with CTA b.
   int g = int(nchunks < size_t(kP2PRings) ? nchunks : size_t(kP2PRings));
   P2PArgs a{static_cast<char *>(buf), nbytes, chunk, peer};
-  if (send) p2p_kernel<true><<<g, kThreads, 0, stream>>>(c->dev(), a);
-  else p2p_kernel<false><<<g, kThreads, 0, stream>>>(c->dev(), a);
+  // The protocol (rings, slots, chunking) is a function of the message size alone; HOW this side
+  // moves its bytes is a local choice: the bulk-copy unit when the tensor is 16-byte aligned, a
+  // whole number of 16-byte units and the chunks are big enough to be worth a TMA pipeline.
+  const long long pb = c->params[B200_PARAM_P2P_BULK_MIN_CHUNK];
+  const size_t bulk_min_chunk = pb >= 0 ? size_t(pb) : (size_t(32) << 10);
+  const bool bulk = is_aligned16(buf) && (nbytes & 15) == 0 && chunk >= bulk_min_chunk && pb != 0;
+  if (bulk) {
+    auto k = send ? p2p_bulk_kernel<true> : p2p_bulk_kernel<false>;
+    if (int rc2 = set_dyn_smem(c->device, reinterpret_cast<const void *>(k))) return rc2;
+    k<<<g, kThreads, kBulkSmemBytes, stream>>>(c->dev(), a);
+  } else if (send) {
+    p2p_kernel<true><<<g, kThreads, 0, stream>>>(c->dev(), a);
+  } else {
+    p2p_kernel<false><<<g, kThreads, 0, stream>>>(c->dev(), a);
+  }
   B200_LAUNCH_CHECK(c);
   return B200_OK;
 }
