@@ -43,39 +43,56 @@ struct PipeArgs {
 };
 
 struct PipeGeom {
-  size_t S, C, K;
-  int G;       // copy CTAs per role
+  size_t S, C;
+  uint32_t K;  // chunks
+  uint32_t G;  // copy CTAs per role
   uint32_t m;  // tiles per copy CTA per full chunk
 };
 __device__ __forceinline__ PipeGeom make_geom(const PipeArgs &a) {
   PipeGeom g;
   g.S = a.nbytes;
   g.C = a.chunk_bytes;
-  g.K = (g.S + g.C - 1) / g.C;
-  g.G = a.copy_ctas;
+  g.K = uint32_t((g.S + g.C - 1) / g.C);
+  g.G = uint32_t(a.copy_ctas);
   g.m = uint32_t(g.C / (size_t(g.G) * kBulkTile));
   return g;
 }
-__device__ __forceinline__ size_t chunk_len(const PipeGeom &g, size_t k) {
-  const size_t lo = k * g.C;
+__device__ __forceinline__ size_t chunk_len(const PipeGeom &g, uint32_t k) {
+  const size_t lo = size_t(k) * g.C;
   return (g.S - lo) < g.C ? (g.S - lo) : g.C;
 }
-// byte offset of the i-th tile of copy CTA j (>= S: past the end)
-__device__ __forceinline__ size_t tile_off(const PipeGeom &g, int j, size_t i) {
-  const size_t k = i / g.m, t = (i % g.m) * size_t(g.G) + size_t(j);
-  return k * g.C + t * kBulkTile;
+// byte offset of the i-th tile of copy CTA j (tiles past the end of the message are never asked for)
+__device__ __forceinline__ size_t tile_off(const PipeGeom &g, uint32_t j, uint32_t i) {
+  const uint32_t k = i / g.m, t = (i - k * g.m) * g.G + j;
+  return size_t(k) * g.C + size_t(t) * kBulkTile;
 }
-__device__ __forceinline__ size_t tiles_of_cta(const PipeGeom &g, int j) {
+__device__ __forceinline__ uint32_t tile_len(const PipeGeom &g, size_t off) {
+  return uint32_t((g.S - off) < size_t(kBulkTile) ? (g.S - off) : size_t(kBulkTile));
+}
+__device__ __forceinline__ uint32_t tiles_of_cta(const PipeGeom &g, uint32_t j) {
   const size_t full = g.S / g.C, rem = g.S - full * g.C;
-  size_t nt = full * g.m;
+  uint32_t nt = uint32_t(full) * g.m;
   for (uint32_t q = 0; q < g.m; ++q)
     if ((size_t(q) * g.G + size_t(j)) * kBulkTile < rem) ++nt;
   return nt;
 }
 // copy CTAs that own at least one tile of chunk k (= arrivals expected on its counter)
-__device__ __forceinline__ uint32_t copy_arrivals(const PipeGeom &g, size_t k) {
+__device__ __forceinline__ uint32_t copy_arrivals(const PipeGeom &g, uint32_t k) {
   const size_t tiles = (chunk_len(g, k) + kBulkTile - 1) / kBulkTile;
   return uint32_t(tiles < size_t(g.G) ? tiles : size_t(g.G));
+}
+
+// Copy CTAs split the work between two threads: thread 0 drives the bulk-copy unit and only
+// bumps a shared-memory mailbox when its last tile of a chunk has completed; thread 32 turns
+// mailbox increments into chunk arrivals and flags, so the system-scope fences that publishing
+// needs never stall the copy pipeline.  A copy CTA owns tiles in chunks 0 .. nchunks-1 (in order).
+struct CopyMailbox {
+  volatile uint32_t chunks_done;
+  volatile int stop;
+};
+__device__ __forceinline__ void mailbox_post(CopyMailbox *mb, uint32_t chunks_done) {
+  __threadfence_block();
+  mb->chunks_done = chunks_done;
 }
 
 // One thread: count this CTA's arrival on a chunk; the last arriver re-zeroes the counter and
@@ -99,20 +116,20 @@ __device__ __forceinline__ void signal_all(const DevComm &c, size_t flag_word, u
   }
 }
 // All threads: wait until every rank's flag of chunk k reached `value`.
-__device__ __forceinline__ bool cta_wait_chunk(const DevComm &c, size_t flag_base, size_t k, uint32_t value) {
+__device__ __forceinline__ bool cta_wait_chunk(const DevComm &c, size_t flag_base, uint32_t k, uint32_t value) {
   __shared__ int ok_flag;
   if (threadIdx.x == 0) ok_flag = 1;
   __syncthreads();
   if (threadIdx.x < c.world) {
-    if (!wait_flag_ge(c, c.sig[c.rank] + flag_base + k * kMaxRanks + threadIdx.x, value)) ok_flag = 0;
+    if (!wait_flag_ge(c, c.sig[c.rank] + flag_base + size_t(k) * kMaxRanks + threadIdx.x, value)) ok_flag = 0;
   }
   __syncthreads();
   return ok_flag != 0;
 }
 // One thread (the bulk-copy driver): same test, optionally non-blocking.
-__device__ __forceinline__ int thread_wait_chunk(const DevComm &c, size_t flag_base, size_t k, uint32_t value,
+__device__ __forceinline__ int thread_wait_chunk(const DevComm &c, size_t flag_base, uint32_t k, uint32_t value,
                                                  bool block) {
-  const uint32_t *f = c.sig[c.rank] + flag_base + k * kMaxRanks;
+  const uint32_t *f = c.sig[c.rank] + flag_base + size_t(k) * kMaxRanks;
   for (int p = 0; p < c.world; ++p) {
     if (block) {
       if (!wait_flag_ge(c, f + p, value)) return -1;
@@ -121,6 +138,26 @@ __device__ __forceinline__ int thread_wait_chunk(const DevComm &c, size_t flag_b
     }
   }
   return 1;
+}
+
+// Flag thread of a copy-in / push CTA: publish flag0 of every chunk this CTA finished.
+__device__ __forceinline__ void copy_flag_thread(const DevComm &c, const PipeGeom &g, CopyMailbox *mb,
+                                                 uint32_t nchunks, uint32_t value) {
+  uint32_t published = 0;
+  while (published < nchunks) {
+    const uint32_t avail = mb->chunks_done;
+    if (avail == published) {
+      if (mb->stop) break;
+      __nanosleep(100);
+      continue;
+    }
+    __threadfence_block();
+    fence_proxy_async();
+    for (; published < avail; ++published) {
+      if (chunk_arrive(&c.st->pipe_cnt[0][published], copy_arrivals(g, published)))
+        signal_all(c, kSigPipe0 + size_t(published) * kMaxRanks, value);
+    }
+  }
 }
 
 constexpr int kItemUnroll = 4;
@@ -138,37 +175,41 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
   const size_t off = staging_slot_offset(launch, a.staging_bytes);
   const PipeGeom g = make_geom(a);
   const int n = c.world, r = c.rank;
-  const int G = g.G, Gr = int(gridDim.x) - 2 * G;
+  const int G = int(g.G), Gr = int(gridDim.x) - 2 * G;
   const int b = blockIdx.x;
 
   if (b < G) {
     // ---- copy-in -------------------------------------------------------------------------
-    const BulkRing ring = bulk_ring_init(dyn_smem);
+    __shared__ CopyMailbox mb;
     if (threadIdx.x == 0) {
-      const int j = b;
-      const size_t nt = tiles_of_cta(g, j);
+      mb.chunks_done = 0;
+      mb.stop = 0;
+    }
+    const BulkRing ring = bulk_ring_init(dyn_smem);
+    const uint32_t j = uint32_t(b);
+    const uint32_t nt = tiles_of_cta(g, j);
+    const uint32_t my_chunks = nt ? (nt - 1) / g.m + 1 : 0;
+    if (threadIdx.x == 0) {
       char *slot = c.data[r] + off;
-      bulk_copy_run(
-          ring, nt, [&](size_t i) {
+      const bool ok = bulk_copy_run<kBulkLagLocal>(
+          ring, nt, [&](uint32_t i) {
             const size_t o = tile_off(g, j, i);
-            return BulkTileDesc{a.in + o, uint32_t((g.S - o) < size_t(kBulkTile) ? (g.S - o) : size_t(kBulkTile))};
+            return BulkTileDesc{a.in + o, tile_len(g, o)};
           },
-          [&](size_t i, uint32_t smem, uint32_t bytes) { bulk_s2g(slot + tile_off(g, j, i), smem, bytes); },
-          [&](size_t, bool) { return 1; },
-          [&](size_t i) {
-            if ((i % g.m) == g.m - 1 || i + 1 == nt) {  // this CTA's last tile of chunk k
-              const size_t k = i / g.m;
-              fence_proxy_async();
-              if (chunk_arrive(&c.st->pipe_cnt[0][k], copy_arrivals(g, k)))
-                signal_all(c, kSigPipe0 + k * kMaxRanks, ep + 1);
-            }
+          [&](uint32_t i, uint32_t smem, uint32_t bytes) { bulk_s2g(slot + tile_off(g, j, i), smem, bytes); },
+          [&](uint32_t, bool) { return 1; },
+          [&](uint32_t i) {
+            if ((i + 1) % g.m == 0 || i + 1 == nt) mailbox_post(&mb, i / g.m + 1);  // last tile of a chunk
           });
+      if (!ok) mb.stop = 1;
+    } else if (threadIdx.x == 32) {
+      copy_flag_thread(c, g, &mb, my_chunks, ep + 1);
     }
   } else if (b < G + Gr) {
     // ---- reduce ------------------------------------------------------------------------------
     const int me = b - G;
     size_t item_base = 0;  // global index of chunk k's first work item
-    for (size_t k = 0; k < g.K; ++k) {
+    for (uint32_t k = 0; k < g.K; ++k) {
       const size_t cu = chunk_len(g, k) >> 4;           // units in this chunk
       const size_t lo = cu * size_t(r) / size_t(n);     // this rank's stripe
       const size_t hi = cu * size_t(r + 1) / size_t(n);
@@ -178,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
       item_base += nitems;
       if (it >= nitems) continue;
       if (!cta_wait_chunk(c, kSigPipe0, k, ep + 1)) break;
-      const size_t cbase = off + k * g.C;
+      const size_t cbase = off + size_t(k) * g.C;
       for (; it < nitems; it += size_t(Gr)) {
         const size_t u0 = lo + it * kItemUnits + threadIdx.x;
         if (NVLS) {
@@ -229,25 +270,25 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
         }
         __syncthreads();
         if (threadIdx.x == 0 && chunk_arrive(&c.st->pipe_cnt[1][k], uint32_t(nitems)))
-          signal_all(c, kSigPipe1 + k * kMaxRanks, ep + 2);
+          signal_all(c, kSigPipe1 + size_t(k) * kMaxRanks, ep + 2);
       }
     }
   } else {
     // ---- copy-out ------------------------------------------------------------------------
     const BulkRing ring = bulk_ring_init(dyn_smem);
     if (threadIdx.x == 0) {
-      const int j = b - G - Gr;
-      const size_t nt = tiles_of_cta(g, j);
+      const uint32_t j = uint32_t(b - G - Gr);
+      const uint32_t nt = tiles_of_cta(g, j);
       const char *slot = c.data[r] + off;
-      size_t ready = 0;  // chunks [0, ready) are published by every rank
-      bulk_copy_run(
-          ring, nt, [&](size_t i) {
+      uint32_t ready = 0;  // chunks [0, ready) are published by every rank
+      bulk_copy_run<kBulkLagLocal>(
+          ring, nt, [&](uint32_t i) {
             const size_t o = tile_off(g, j, i);
-            return BulkTileDesc{slot + o, uint32_t((g.S - o) < size_t(kBulkTile) ? (g.S - o) : size_t(kBulkTile))};
+            return BulkTileDesc{slot + o, tile_len(g, o)};
           },
-          [&](size_t i, uint32_t smem, uint32_t bytes) { bulk_s2g(a.out + tile_off(g, j, i), smem, bytes); },
-          [&](size_t i, bool block) {
-            const size_t k = i / g.m;
+          [&](uint32_t i, uint32_t smem, uint32_t bytes) { bulk_s2g(a.out + tile_off(g, j, i), smem, bytes); },
+          [&](uint32_t i, bool block) {
+            const uint32_t k = i / g.m;
             if (k < ready) return 1;
             const int st = thread_wait_chunk(c, kSigPipe1, k, ep + 2, block);
             if (st == 1) {
@@ -256,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
             }
             return st;
           },
-          [&](size_t) {});
+          [&](uint32_t) {});
     }
   }
   finish_launch(c);
@@ -308,22 +349,28 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_push_kernel(DevComm c, 
   const size_t off = staging_slot_offset(launch, a.staging_bytes);
   const PipeGeom g = make_geom(a);
   const int n = c.world, r = c.rank;
-  const int G = g.G, Gr = int(gridDim.x) - G;
+  const int G = int(g.G), Gr = int(gridDim.x) - G;
   const int b = blockIdx.x;
   const size_t sub = g.S;  // bytes per source sub-slot (S is a multiple of 16)
 
   if (b < G) {
     // ---- push: my tensor into every peer's slot, sub-slot "me" ------------------------------
-    const BulkRing ring = bulk_ring_init(dyn_smem);
+    __shared__ CopyMailbox mb;
     if (threadIdx.x == 0) {
-      const int j = b;
-      const size_t nt = tiles_of_cta(g, j);
-      bulk_copy_run(
-          ring, nt, [&](size_t i) {
+      mb.chunks_done = 0;
+      mb.stop = 0;
+    }
+    const BulkRing ring = bulk_ring_init(dyn_smem);
+    const uint32_t j = uint32_t(b);
+    const uint32_t nt = tiles_of_cta(g, j);
+    const uint32_t my_chunks = nt ? (nt - 1) / g.m + 1 : 0;
+    if (threadIdx.x == 0) {
+      const bool ok = bulk_copy_run<kBulkLagRemote>(
+          ring, nt, [&](uint32_t i) {
             const size_t o = tile_off(g, j, i);
-            return BulkTileDesc{a.in + o, uint32_t((g.S - o) < size_t(kBulkTile) ? (g.S - o) : size_t(kBulkTile))};
+            return BulkTileDesc{a.in + o, tile_len(g, o)};
           },
-          [&](size_t i, uint32_t smem, uint32_t bytes) {
+          [&](uint32_t i, uint32_t smem, uint32_t bytes) {
             const size_t o = tile_off(g, j, i);
             for (int q = 1; q < n; ++q) {
               int p = r + q;
@@ -331,21 +378,19 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_push_kernel(DevComm c, 
               bulk_s2g(c.data[p] + off + size_t(r < p ? r : r - 1) * sub + o, smem, bytes);
             }
           },
-          [&](size_t, bool) { return 1; },
-          [&](size_t i) {
-            if ((i % g.m) == g.m - 1 || i + 1 == nt) {
-              const size_t k = i / g.m;
-              fence_proxy_async();
-              if (chunk_arrive(&c.st->pipe_cnt[0][k], copy_arrivals(g, k)))
-                signal_all(c, kSigPipe0 + k * kMaxRanks, ep + 1);
-            }
+          [&](uint32_t, bool) { return 1; },
+          [&](uint32_t i) {
+            if ((i + 1) % g.m == 0 || i + 1 == nt) mailbox_post(&mb, i / g.m + 1);
           });
+      if (!ok) mb.stop = 1;
+    } else if (threadIdx.x == 32) {
+      copy_flag_thread(c, g, &mb, my_chunks, ep + 1);
     }
   } else {
     // ---- reduce: own tensor (op) what the peers pushed, straight into the caller's tensor ---
     const int me = b - G;
     size_t item_base = 0;
-    for (size_t k = 0; k < g.K; ++k) {
+    for (uint32_t k = 0; k < g.K; ++k) {
       const size_t cu = chunk_len(g, k) >> 4;
       const size_t nitems = (cu + kItemUnits - 1) / kItemUnits;
       size_t it = (size_t(me) + size_t(Gr) - item_base % size_t(Gr)) % size_t(Gr);
@@ -354,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_push_kernel(DevComm c, 
       // flag0[k][p] for p != r: p's chunk has landed here; p == r: the local push CTAs are done
       // READING chunk k of the caller's tensor, so it may be overwritten in place.
       if (!cta_wait_chunk(c, kSigPipe0, k, ep + 1)) break;
-      const size_t ubase = (k * g.C) >> 4;
+      const size_t ubase = (size_t(k) * g.C) >> 4;
       for (; it < nitems; it += size_t(Gr)) {
         const size_t u0 = it * kItemUnits + threadIdx.x;
         if (n == 2) {
@@ -404,7 +449,7 @@ size_t pipe_max_bytes(const b200_comm *c, int variant) {
 size_t pipe_chunk_bytes(const b200_comm *c) {
   const long long v = c->params[B200_PARAM_PIPE_CHUNK_BYTES];
   size_t C = v > 0 ? size_t(v) : (size_t(1) << 20);
-  const size_t quantum = size_t(64) * kBulkTile;  // any power-of-two copy-CTA count up to 64 divides it
+  const size_t quantum = size_t(32) * kBulkTile;  // any power-of-two copy-CTA count up to 32 divides it
   return round_up(C, quantum);
 }
 
@@ -426,7 +471,7 @@ int launch_allreduce_pipe(b200_comm *c, const char *in, char *out, size_t nbytes
       return B200_ERR_UNSUPPORTED;
     }
   }
-  G = pow2_floor(G > 64 ? 64 : G);
+  G = pow2_floor(G > 32 ? 32 : G);
   a.copy_ctas = G;
   const int grid = roles * G + Gr;
   DevComm dc = c->dev();

@@ -17,10 +17,17 @@
 
 namespace b200 {
 
-constexpr int kBulkTile = 16 << 10;  // bytes per tile
-constexpr int kBulkStages = 12;      // ring depth (12 x 16 KiB = 192 KiB of shared memory)
-constexpr int kBulkLookahead = 4;    // loads issued ahead of the store cursor
-constexpr int kBulkPending = kBulkStages - kBulkLookahead - 1;  // store groups allowed in flight
+constexpr int kBulkTile = 32 << 10;  // bytes per tile
+constexpr int kBulkStages = 6;       // ring depth (6 x 32 KiB = 192 KiB of shared memory)
+constexpr int kBulkLookahead = 3;    // loads issued ahead of the store cursor
+// A ring buffer is free again as soon as its store has READ it (wait_group.read); the store's
+// global writes may still be in flight then.  Measured on B200 (profiles/r02): a bulk store to a
+// peer over NVLink takes ~6 us to COMPLETE, so bounding the stores in flight by the ring depth
+// (12 x 16 KiB in the first version) capped a CTA at 18 GB/s.  Completion is therefore tracked
+// separately and lazily: done(i) is reported once tile i + D has been issued (wait_group D).
+constexpr int kBulkReadPending = kBulkStages - kBulkLookahead - 1;  // stores that may still be reading the ring
+constexpr int kBulkLagRemote = 10;  // completion lag D for stores that cross NVLink
+constexpr int kBulkLagLocal = 3;    // ... and for stores into local HBM
 constexpr size_t kBulkSmemBytes = size_t(kBulkStages) * kBulkTile + 16 * kBulkStages;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -58,6 +65,10 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait() {  // all but the N most recent groups have COMPLETED (writes done)
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // all but the N most recent groups have read their source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 // orders async-proxy accesses (bulk copies) against generic-proxy accesses (ld/st, flags)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -97,15 +108,21 @@ __device__ __forceinline__ BulkRing bulk_ring_init(char *dyn_smem) {
 //                     can make progress it drains its pending stores (so every done() it owes has
 //                     been delivered -- a peer may be waiting for exactly that) and asks again with
 //                     block = true.
-//   done(i)        -> called, in order, once the STORE of tile i has completed
+//   done(i)        -> called, in order, once the STORE of tile i has completed (reported lazily:
+//                     when tile i + LAG has been issued, or when the engine drains)
 // Returns false when abandoned.
-template <typename TileFn, typename EmitFn, typename GateFn, typename DoneFn>
-__device__ __forceinline__ bool bulk_copy_run(const BulkRing &ring, size_t ntiles, TileFn tile, EmitFn emit,
+// Tile indices are 32-bit on purpose: the callers' index arithmetic (tile -> chunk, offset) then
+// compiles to 32-bit divisions instead of the ~10x slower 64-bit ones, which matters because one
+// thread issues every tile.
+template <int LAG, typename TileFn, typename EmitFn, typename GateFn, typename DoneFn>
+__device__ __forceinline__ bool bulk_copy_run(const BulkRing &ring, uint32_t ntiles, TileFn tile, EmitFn emit,
                                               GateFn gate, DoneFn done) {
-  size_t load_i = 0, store_j = 0, completed = 0;
+  uint32_t load_i = 0, store_j = 0, completed = 0;
   bool ok = true;
   while (store_j < ntiles) {
-    while (load_i < ntiles && load_i - store_j < size_t(kBulkLookahead) && load_i - completed < size_t(kBulkStages)) {
+    // ring buffer of tile load_i was last used by tile load_i - kBulkStages <= store_j - 1 -
+    // kBulkReadPending, which the wait_group.read below has retired
+    while (load_i < ntiles && load_i - store_j < uint32_t(kBulkLookahead)) {
       const int g = gate(load_i, false);
       if (g < 0) ok = false;
       if (g <= 0) break;
@@ -124,8 +141,11 @@ __device__ __forceinline__ bool bulk_copy_run(const BulkRing &ring, size_t ntile
       emit(store_j, ring.tiles + uint32_t(s) * kBulkTile, d.bytes);
       bulk_commit();
       ++store_j;
-      bulk_wait<kBulkPending>();
-      for (; completed + kBulkPending < store_j; ++completed) done(completed);
+      bulk_wait_read<kBulkReadPending>();
+      if (completed + LAG < store_j) {
+        bulk_wait<LAG>();
+        for (; completed + LAG < store_j; ++completed) done(completed);
+      }
     } else {
       // nothing in flight towards shared memory and the next source is not ready
       bulk_wait<0>();

@@ -24,6 +24,8 @@
 //                     so <= 16 CTAs fill the link where the ld/st kernel needed 64; a second
 //                     thread publishes the ready / ack flags so the copy thread never waits for a
 //                     system-scope fence.
+#include <type_traits>
+
 #include "bulk_copy.cuh"
 #include "kernel_utils.cuh"
 #include "pipe.h"
@@ -158,54 +160,59 @@ __global__ void __launch_bounds__(kThreads, 1) p2p_bulk_kernel(DevComm c, P2PArg
   }
   const BulkRing br = bulk_ring_init(dyn_smem);  // contains the __syncthreads
 
-  const size_t tpc = (chunk + kBulkTile - 1) / kBulkTile;  // tiles of a full chunk
-  auto chunk_lo = [&](size_t q) { return (size_t(b) + q * size_t(G)) * chunk; };
-  auto chunk_len = [&](size_t q) {
+  const uint32_t tpc = uint32_t((chunk + kBulkTile - 1) / kBulkTile);  // tiles of a full chunk
+  const uint32_t nq32 = uint32_t(nq);
+  auto chunk_lo = [&](uint32_t q) { return (size_t(b) + size_t(q) * size_t(G)) * chunk; };
+  auto chunk_len = [&](uint32_t q) {
     const size_t lo = chunk_lo(q);
     return (a.nbytes - lo) < chunk ? (a.nbytes - lo) : chunk;
   };
   if (threadIdx.x == 0 && nq > 0) {
     // ---- copy thread ---------------------------------------------------------------------
-    const size_t last_tiles = (chunk_len(nq - 1) + kBulkTile - 1) / kBulkTile;
-    const size_t nt = (nq - 1) * tpc + last_tiles;
-    size_t gated = 0;  // chunks [0, gated) passed their gate
-    auto slot_of = [&](size_t q) { return ring + size_t((seq0 + uint32_t(q)) % kP2PSlots) * slot_bytes; };
-    const bool ok = bulk_copy_run(
-        br, nt,
-        [&](size_t i) {
-          const size_t q = i / tpc, t = i % tpc;
-          const size_t len = chunk_len(q), o = t * kBulkTile;
-          const uint32_t bytes = uint32_t((len - o) < size_t(kBulkTile) ? (len - o) : size_t(kBulkTile));
-          return BulkTileDesc{SEND ? a.buf + chunk_lo(q) + o : slot_of(q) + o, bytes};
-        },
-        [&](size_t i, uint32_t smem, uint32_t bytes) {
-          const size_t q = i / tpc, o = (i % tpc) * kBulkTile;
-          bulk_s2g(SEND ? slot_of(q) + o : a.buf + chunk_lo(q) + o, smem, bytes);
-        },
-        [&](size_t i, bool block) {
-          const size_t q = i / tpc;
-          if (q < gated) return 1;
-          const uint32_t seq = seq0 + uint32_t(q);
-          // sender: the slot was consumed (ack in MY pad); receiver: the chunk landed (ready in MY pad)
-          const uint32_t *flag = SEND ? ack : ready + seq % kP2PSlots;
-          const uint32_t target = SEND ? seq + 1u - kP2PSlots : seq + 1u;
-          if (block) {
-            if (!wait_flag_ge(c, flag, target)) return -1;
-          } else if (int32_t(ld_acquire_sys(flag) - target) < 0) {
-            return 0;
-          }
-          if (!SEND) fence_proxy_async();  // the peer's stores before our bulk reads
-          gated = q + 1;
-          return 1;
-        },
-        [&](size_t i) {
-          const size_t q = i / tpc, t = i % tpc;
-          const size_t tiles = (chunk_len(q) + kBulkTile - 1) / kBulkTile;
-          if (t + 1 == tiles) {
-            __threadfence_block();
-            mailbox = uint32_t(q + 1);
-          }
-        });
+    const uint32_t last_tiles = uint32_t((chunk_len(nq32 - 1) + kBulkTile - 1) / kBulkTile);
+    const uint32_t nt = (nq32 - 1) * tpc + last_tiles;
+    uint32_t gated = 0;  // chunks [0, gated) passed their gate
+    auto slot_of = [&](uint32_t q) { return ring + size_t((seq0 + q) % kP2PSlots) * slot_bytes; };
+    auto run = [&](auto lag) {
+      return bulk_copy_run<decltype(lag)::value>(
+          br, nt,
+          [&](uint32_t i) {
+            const uint32_t q = i / tpc, t = i - q * tpc;
+            const size_t len = chunk_len(q), o = size_t(t) * kBulkTile;
+            const uint32_t bytes = uint32_t((len - o) < size_t(kBulkTile) ? (len - o) : size_t(kBulkTile));
+            return BulkTileDesc{SEND ? a.buf + chunk_lo(q) + o : slot_of(q) + o, bytes};
+          },
+          [&](uint32_t i, uint32_t smem, uint32_t bytes) {
+            const uint32_t q = i / tpc;
+            const size_t o = size_t(i - q * tpc) * kBulkTile;
+            bulk_s2g(SEND ? slot_of(q) + o : a.buf + chunk_lo(q) + o, smem, bytes);
+          },
+          [&](uint32_t i, bool block) {
+            const uint32_t q = i / tpc;
+            if (q < gated) return 1;
+            const uint32_t seq = seq0 + q;
+            // sender: the slot was consumed (ack in MY pad); receiver: the chunk landed (ready in MY pad)
+            const uint32_t *flag = SEND ? ack : ready + seq % kP2PSlots;
+            const uint32_t target = SEND ? seq + 1u - kP2PSlots : seq + 1u;
+            if (block) {
+              if (!wait_flag_ge(c, flag, target)) return -1;
+            } else if (int32_t(ld_acquire_sys(flag) - target) < 0) {
+              return 0;
+            }
+            if (!SEND) fence_proxy_async();  // the peer's stores before our bulk reads
+            gated = q + 1;
+            return 1;
+          },
+          [&](uint32_t i) {
+            if ((i + 1) % tpc == 0 || i + 1 == nt) {  // last tile of a chunk
+              __threadfence_block();
+              mailbox = i / tpc + 1;
+            }
+          });
+    };
+    // the sender's stores cross NVLink (long completion latency), the receiver's stay in local HBM
+    const bool ok = SEND ? run(std::integral_constant<int, kBulkLagRemote>{})
+                         : run(std::integral_constant<int, kBulkLagLocal>{});
     if (!ok) stop = 1;
   } else if (threadIdx.x == 32 && nq > 0) {
     // ---- flag thread: publishes "ready" (sender) / "ack" (receiver) for completed chunks ------
