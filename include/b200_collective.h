@@ -210,6 +210,13 @@ uint64_t b200_comm_launch_count(b200_comm_t comm);
 /* Tuning knob: force the CTA count used by collectives (0 = automatic). */
 int b200_comm_set_blocks(b200_comm_t comm, int nblocks);
 
+/* In-kernel event trace (profiling aid, off by default): allocates room for `capacity` events
+ * (0 frees it); instrumented kernels then record (globaltimer ns, CTA, event id, argument).
+ * b200_comm_trace_read synchronises the device, copies up to max_events events (2 x u64 each:
+ * ns, blockIdx << 40 | event << 32 | argument) and returns how many; `reset` != 0 clears it. */
+int b200_comm_trace_enable(b200_comm_t comm, unsigned int capacity);
+int b200_comm_trace_read(b200_comm_t comm, unsigned long long *out, unsigned int max_events, int reset);
+
 /* Tuning parameters (must be set identically on every rank; -1 restores the default). */
 typedef enum {
   B200_PARAM_ONESHOT_MAX_BYTES = 0, /* all-reduce messages up to this size use the one-shot kernel */

@@ -139,6 +139,19 @@ class B200Comm:
         """Tuning knob (``N.PARAM_*``); must be set identically on every rank."""
         N.check(self._lib.b200_comm_set_param(self._h, int(param), int(value)))
 
+    def trace_enable(self, capacity: int) -> None:
+        """Profiling aid: let instrumented kernels record up to ``capacity`` timestamped events."""
+        N.check(self._lib.b200_comm_trace_enable(self._h, int(capacity)))
+
+    def trace_read(self, max_events: int = 1 << 20, reset: bool = True):
+        """-> list of (ns, cta, event, arg) recorded since the last reset (synchronises the device)."""
+        buf = (ctypes.c_ulonglong * (2 * max_events))()
+        n = self._lib.b200_comm_trace_read(self._h, buf, max_events, 1 if reset else 0)
+        if n < 0:
+            N.check(n)
+        return [(buf[2 * i], buf[2 * i + 1] >> 40, (buf[2 * i + 1] >> 32) & 0xFF, buf[2 * i + 1] & 0xFFFFFFFF)
+                for i in range(n)]
+
     def status(self) -> int:
         return int(self._lib.b200_comm_status(self._h))
 

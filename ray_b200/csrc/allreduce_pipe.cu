@@ -96,17 +96,22 @@ __device__ __forceinline__ void mailbox_post(CopyMailbox *mb, uint32_t chunks_do
 }
 
 // One thread: count this CTA's arrival on a chunk; the last arriver re-zeroes the counter and
-// returns true with every CTA's writes ordered before whatever it stores next (system scope:
-// the readers are other GPUs).
-__device__ __forceinline__ bool chunk_arrive(uint32_t *cnt, uint32_t expected) {
-  __threadfence_system();
+// returns true.  The caller has executed __threadfence_system() after the writes the arrival
+// stands for (one fence may cover a batch of arrivals: with bulk stores to a peer in flight a
+// system-scope fence costs ~4 us -- measured, profiles/r02/trace_push_v1.log), so by the time any
+// CTA observes the final count every contribution has been performed system-wide, and the flag
+// stores that follow the observation are issued after it.
+__device__ __forceinline__ bool chunk_arrive_fenced(uint32_t *cnt, uint32_t expected) {
   const uint32_t old = atomicAdd(cnt, 1u);
   if (old + 1u == expected) {
     *cnt = 0;
-    __threadfence_system();
     return true;
   }
   return false;
+}
+__device__ __forceinline__ bool chunk_arrive(uint32_t *cnt, uint32_t expected) {
+  __threadfence_system();
+  return chunk_arrive_fenced(cnt, expected);
 }
 __device__ __forceinline__ void signal_all(const DevComm &c, size_t flag_word, uint32_t value) {
   for (int i = 0; i < c.world; ++i) {
@@ -152,10 +157,17 @@ __device__ __forceinline__ void copy_flag_thread(const DevComm &c, const PipeGeo
       continue;
     }
     __threadfence_block();
+    trace_event(c, 9, avail);
     fence_proxy_async();
+    trace_event(c, 10, avail);
+    __threadfence_system();  // ONE fence for every chunk completed so far
+    trace_event(c, 13, avail);
     for (; published < avail; ++published) {
-      if (chunk_arrive(&c.st->pipe_cnt[0][published], copy_arrivals(g, published)))
+      if (chunk_arrive_fenced(&c.st->pipe_cnt[0][published], copy_arrivals(g, published))) {
         signal_all(c, kSigPipe0 + size_t(published) * kMaxRanks, value);
+        trace_event(c, 12, published);
+      }
+      trace_event(c, 11, published);
     }
   }
 }
@@ -191,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
     const uint32_t my_chunks = nt ? (nt - 1) / g.m + 1 : 0;
     if (threadIdx.x == 0) {
       char *slot = c.data[r] + off;
-      const bool ok = bulk_copy_run<kBulkLagLocal>(
+      const bool ok = bulk_copy_run<BulkLocal>(
           ring, nt, [&](uint32_t i) {
             const size_t o = tile_off(g, j, i);
             return BulkTileDesc{a.in + o, tile_len(g, o)};
@@ -200,7 +212,8 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
           [&](uint32_t, bool) { return 1; },
           [&](uint32_t i) {
             if ((i + 1) % g.m == 0 || i + 1 == nt) mailbox_post(&mb, i / g.m + 1);  // last tile of a chunk
-          });
+          },
+          [&](unsigned ev, unsigned arg) { trace_event(c, ev, arg); });
       if (!ok) mb.stop = 1;
     } else if (threadIdx.x == 32) {
       copy_flag_thread(c, g, &mb, my_chunks, ep + 1);
@@ -218,7 +231,9 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
       size_t it = (size_t(me) + size_t(Gr) - item_base % size_t(Gr)) % size_t(Gr);
       item_base += nitems;
       if (it >= nitems) continue;
+      if (threadIdx.x == 0) trace_event(c, 20, k);
       if (!cta_wait_chunk(c, kSigPipe0, k, ep + 1)) break;
+      if (threadIdx.x == 0) trace_event(c, 21, k);
       const size_t cbase = off + size_t(k) * g.C;
       for (; it < nitems; it += size_t(Gr)) {
         const size_t u0 = lo + it * kItemUnits + threadIdx.x;
@@ -269,8 +284,12 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
           }
         }
         __syncthreads();
-        if (threadIdx.x == 0 && chunk_arrive(&c.st->pipe_cnt[1][k], uint32_t(nitems)))
-          signal_all(c, kSigPipe1 + size_t(k) * kMaxRanks, ep + 2);
+        if (threadIdx.x == 0) {
+          trace_event(c, 22, k);
+          if (chunk_arrive(&c.st->pipe_cnt[1][k], uint32_t(nitems)))
+            signal_all(c, kSigPipe1 + size_t(k) * kMaxRanks, ep + 2);
+          trace_event(c, 23, k);
+        }
       }
     }
   } else {
@@ -281,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
       const uint32_t nt = tiles_of_cta(g, j);
       const char *slot = c.data[r] + off;
       uint32_t ready = 0;  // chunks [0, ready) are published by every rank
-      bulk_copy_run<kBulkLagLocal>(
+      bulk_copy_run<BulkLocal>(
           ring, nt, [&](uint32_t i) {
             const size_t o = tile_off(g, j, i);
             return BulkTileDesc{slot + o, tile_len(g, o)};
@@ -297,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
             }
             return st;
           },
-          [&](uint32_t) {});
+          [&](uint32_t) {}, [&](unsigned ev, unsigned arg) { trace_event(c, 40 + ev, arg); });
     }
   }
   finish_launch(c);
@@ -365,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_push_kernel(DevComm c, 
     const uint32_t nt = tiles_of_cta(g, j);
     const uint32_t my_chunks = nt ? (nt - 1) / g.m + 1 : 0;
     if (threadIdx.x == 0) {
-      const bool ok = bulk_copy_run<kBulkLagRemote>(
+      const bool ok = bulk_copy_run<BulkRemote>(
           ring, nt, [&](uint32_t i) {
             const size_t o = tile_off(g, j, i);
             return BulkTileDesc{a.in + o, tile_len(g, o)};
@@ -381,7 +400,8 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_push_kernel(DevComm c, 
           [&](uint32_t, bool) { return 1; },
           [&](uint32_t i) {
             if ((i + 1) % g.m == 0 || i + 1 == nt) mailbox_post(&mb, i / g.m + 1);
-          });
+          },
+          [&](unsigned ev, unsigned arg) { trace_event(c, ev, arg); });
       if (!ok) mb.stop = 1;
     } else if (threadIdx.x == 32) {
       copy_flag_thread(c, g, &mb, my_chunks, ep + 1);
@@ -398,7 +418,9 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_push_kernel(DevComm c, 
       if (it >= nitems) continue;
       // flag0[k][p] for p != r: p's chunk has landed here; p == r: the local push CTAs are done
       // READING chunk k of the caller's tensor, so it may be overwritten in place.
+      if (threadIdx.x == 0) trace_event(c, 20, k);
       if (!cta_wait_chunk(c, kSigPipe0, k, ep + 1)) break;
+      if (threadIdx.x == 0) trace_event(c, 21, k);
       const size_t ubase = (size_t(k) * g.C) >> 4;
       for (; it < nitems; it += size_t(Gr)) {
         const size_t u0 = it * kItemUnits + threadIdx.x;
@@ -409,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_push_kernel(DevComm c, 
           for (int q = 0; q < kItemUnroll; ++q)
             push_reduce_item<T, OP, 1, kMaxRanks>(c, a, sub, off, ubase, u0 + size_t(q) * kThreads, cu);
         }
+        if (threadIdx.x == 0) trace_event(c, 22, k);
       }
     }
   }

@@ -452,6 +452,8 @@ b200::DevComm b200_comm::dev() const {
   d.host_status = d_abort + 1;
   d.timeout_ns = (unsigned long long)(cfg.timeout_ms) * 1000000ull;
   d.inbox_bytes = inbox_bytes;
+  d.trace = d_trace;
+  d.trace_cap = trace_cap;
   return d;
 }
 
@@ -769,6 +771,7 @@ int b200_comm_destroy(b200_comm_t c) {
   region_destroy(c, &c->ll);
   if (c->d_state) cudaFree(c->d_state);
   if (c->h_abort) cudaFreeHost(c->h_abort);
+  if (c->d_trace) cudaFree(c->d_trace);
   (void)cudaGetLastError();
   {
     std::lock_guard<std::mutex> lk(g_pool_mu);
@@ -887,6 +890,37 @@ int b200_comm_set_blocks(b200_comm_t c, int nblocks) {
   }
   c->forced_blocks = nblocks;
   return B200_OK;
+}
+
+int b200_comm_trace_enable(b200_comm_t c, unsigned int capacity) {
+  if (!c) return B200_ERR_INVALID;
+  B200_CHECK_CUDA(cudaSetDevice(c->device));
+  if (c->d_trace) {
+    B200_CHECK_CUDA(cudaDeviceSynchronize());
+    B200_CHECK_CUDA(cudaFree(c->d_trace));
+    c->d_trace = nullptr;
+    c->trace_cap = 0;
+  }
+  if (capacity == 0) return B200_OK;
+  const size_t bytes = (2 + 2 * size_t(capacity)) * sizeof(unsigned long long);
+  B200_CHECK_CUDA(cudaMalloc(&c->d_trace, bytes));
+  B200_CHECK_CUDA(cudaMemset(c->d_trace, 0, bytes));
+  c->trace_cap = capacity;
+  return B200_OK;
+}
+
+int b200_comm_trace_read(b200_comm_t c, unsigned long long *out, unsigned int max_events, int reset) {
+  if (!c || !out) return B200_ERR_INVALID;
+  if (!c->d_trace) return 0;
+  B200_CHECK_CUDA(cudaSetDevice(c->device));
+  B200_CHECK_CUDA(cudaDeviceSynchronize());
+  unsigned long long n = 0;
+  B200_CHECK_CUDA(cudaMemcpy(&n, c->d_trace, sizeof(n), cudaMemcpyDeviceToHost));
+  if (n > c->trace_cap) n = c->trace_cap;
+  if (n > max_events) n = max_events;
+  if (n) B200_CHECK_CUDA(cudaMemcpy(out, c->d_trace + 2, n * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) B200_CHECK_CUDA(cudaMemset(c->d_trace, 0, 2 * sizeof(unsigned long long)));
+  return int(n);
 }
 
 int b200_comm_set_param(b200_comm_t c, int param, long long value) {

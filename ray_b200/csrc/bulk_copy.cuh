@@ -19,15 +19,25 @@ namespace b200 {
 
 constexpr int kBulkTile = 32 << 10;  // bytes per tile
 constexpr int kBulkStages = 6;       // ring depth (6 x 32 KiB = 192 KiB of shared memory)
-constexpr int kBulkLookahead = 3;    // loads issued ahead of the store cursor
+// loads issued ahead of the store cursor -- measured with scripts/bulk_bench.cu (profiles/r02/
+// bulk_bench.log): local HBM -> local HBM is fastest with 3 (49.6 GB/s per CTA vs 44 with 5),
+// local -> peer over NVLink with 5 (16 CTAs: 702 GB/s vs 577 with 3)
+constexpr int kBulkLookaheadLocal = 3;
+constexpr int kBulkLookaheadRemote = 5;
 // A ring buffer is free again as soon as its store has READ it (wait_group.read); the store's
 // global writes may still be in flight then.  Measured on B200 (profiles/r02): a bulk store to a
 // peer over NVLink takes ~6 us to COMPLETE, so bounding the stores in flight by the ring depth
 // (12 x 16 KiB in the first version) capped a CTA at 18 GB/s.  Completion is therefore tracked
 // separately and lazily: done(i) is reported once tile i + D has been issued (wait_group D).
-constexpr int kBulkReadPending = kBulkStages - kBulkLookahead - 1;  // stores that may still be reading the ring
-constexpr int kBulkLagRemote = 10;  // completion lag D for stores that cross NVLink
-constexpr int kBulkLagLocal = 3;    // ... and for stores into local HBM
+constexpr int kBulkLagRemote = 7;  // completion lag D for stores that cross NVLink
+constexpr int kBulkLagLocal = 3;   // ... and for stores into local HBM
+// the two flavours of the engine
+struct BulkLocal {
+  static constexpr int kLookahead = kBulkLookaheadLocal, kLag = kBulkLagLocal;
+};
+struct BulkRemote {
+  static constexpr int kLookahead = kBulkLookaheadRemote, kLag = kBulkLagRemote;
+};
 constexpr size_t kBulkSmemBytes = size_t(kBulkStages) * kBulkTile + 16 * kBulkStages;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -114,9 +124,17 @@ __device__ __forceinline__ BulkRing bulk_ring_init(char *dyn_smem) {
 // Tile indices are 32-bit on purpose: the callers' index arithmetic (tile -> chunk, offset) then
 // compiles to 32-bit divisions instead of the ~10x slower 64-bit ones, which matters because one
 // thread issues every tile.
-template <int LAG, typename TileFn, typename EmitFn, typename GateFn, typename DoneFn>
+struct BulkNoTrace {
+  __device__ __forceinline__ void operator()(unsigned, unsigned) const {}
+};
+// trace event ids: 1 load issued, 2 load landed + store issued, 3 ring wait passed, 4 done(i)
+// reported, 5 drain (source not ready), 6 blocking gate passed
+template <typename Cfg, typename TileFn, typename EmitFn, typename GateFn, typename DoneFn, typename TraceFn = BulkNoTrace>
 __device__ __forceinline__ bool bulk_copy_run(const BulkRing &ring, uint32_t ntiles, TileFn tile, EmitFn emit,
-                                              GateFn gate, DoneFn done) {
+                                              GateFn gate, DoneFn done, TraceFn tr = TraceFn()) {
+  constexpr int LAG = Cfg::kLag;
+  constexpr int kBulkLookahead = Cfg::kLookahead;
+  constexpr int kBulkReadPending = kBulkStages - kBulkLookahead - 1;  // stores that may still be reading the ring
   uint32_t load_i = 0, store_j = 0, completed = 0;
   bool ok = true;
   while (store_j < ntiles) {
@@ -130,6 +148,7 @@ __device__ __forceinline__ bool bulk_copy_run(const BulkRing &ring, uint32_t nti
       const BulkTileDesc d = tile(load_i);
       mbar_expect_tx(ring.bars + 8 * s, d.bytes);
       bulk_g2s(ring.tiles + uint32_t(s) * kBulkTile, d.src, d.bytes, ring.bars + 8 * s);
+      tr(1, load_i);
       ++load_i;
     }
     if (store_j < load_i) {
@@ -140,14 +159,18 @@ __device__ __forceinline__ bool bulk_copy_run(const BulkRing &ring, uint32_t nti
       const BulkTileDesc d = tile(store_j);
       emit(store_j, ring.tiles + uint32_t(s) * kBulkTile, d.bytes);
       bulk_commit();
+      tr(2, store_j);
       ++store_j;
       bulk_wait_read<kBulkReadPending>();
+      tr(3, store_j);
       if (completed + LAG < store_j) {
         bulk_wait<LAG>();
         for (; completed + LAG < store_j; ++completed) done(completed);
+        tr(4, completed);
       }
     } else {
       // nothing in flight towards shared memory and the next source is not ready
+      tr(5, store_j);
       bulk_wait<0>();
       for (; completed < store_j; ++completed) done(completed);
       if (!ok) break;
@@ -155,6 +178,7 @@ __device__ __forceinline__ bool bulk_copy_run(const BulkRing &ring, uint32_t nti
         ok = false;
         break;
       }
+      tr(6, load_i);
     }
     if (!ok && store_j == load_i) break;
   }

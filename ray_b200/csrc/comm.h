@@ -61,6 +61,8 @@ struct b200_comm {
   b200::LocalState *d_state = nullptr;
   int *h_abort = nullptr;  // cudaHostAlloc'd, mapped
   int *d_abort = nullptr;  // device alias of h_abort
+  unsigned long long *d_trace = nullptr;  // optional kernel event trace
+  unsigned int trace_cap = 0;
 
   // bootstrap endpoint (abstract unix socket served by `server`)
   std::string sock_name;

@@ -73,6 +73,8 @@ struct DevComm {
   volatile int *host_status;  // host-mapped mirror of LocalState::status (read without a CUDA call)
   unsigned long long timeout_ns;
   size_t inbox_bytes;         // per-source inbox size
+  unsigned long long *trace;  // optional event trace (b200_comm_trace_enable), nullptr normally
+  unsigned int trace_cap;     // capacity in events
 };
 
 // ---------------------------------------------------------------------------
@@ -129,6 +131,19 @@ __device__ __forceinline__ void multimem_st(void *mc, uint4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x),
                "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
+}
+
+// Optional in-kernel event trace (debugging / profiling aid; see b200_comm_trace_enable):
+// word 0 of the buffer is the event counter, events are 2 x u64: globaltimer ns, and
+// (blockIdx << 40 | event << 32 | argument).
+__device__ __forceinline__ void trace_event(const DevComm &c, unsigned ev, unsigned arg) {
+  if (c.trace == nullptr) return;
+  const unsigned long long i = atomicAdd(c.trace, 1ull);
+  if (i < c.trace_cap) {
+    c.trace[2 + 2 * i] = globaltimer_ns();
+    c.trace[3 + 2 * i] = (static_cast<unsigned long long>(blockIdx.x) << 40) |
+                         (static_cast<unsigned long long>(ev & 0xffu) << 32) | arg;
+  }
 }
 
 // A kernel that abandons a wait records why: sticky device word (first error wins) plus a

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 1) p2p_bulk_kernel(DevComm c, P2PArg
     uint32_t gated = 0;  // chunks [0, gated) passed their gate
     auto slot_of = [&](uint32_t q) { return ring + size_t((seq0 + q) % kP2PSlots) * slot_bytes; };
     auto run = [&](auto lag) {
-      return bulk_copy_run<decltype(lag)::value>(
+      return bulk_copy_run<decltype(lag)>(
           br, nt,
           [&](uint32_t i) {
             const uint32_t q = i / tpc, t = i - q * tpc;
@@ -211,8 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) p2p_bulk_kernel(DevComm c, P2PArg
           });
     };
     // the sender's stores cross NVLink (long completion latency), the receiver's stay in local HBM
-    const bool ok = SEND ? run(std::integral_constant<int, kBulkLagRemote>{})
-                         : run(std::integral_constant<int, kBulkLagLocal>{});
+    const bool ok = SEND ? run(BulkRemote{}) : run(BulkLocal{});
     if (!ok) stop = 1;
   } else if (threadIdx.x == 32 && nq > 0) {
     // ---- flag thread: publishes "ready" (sender) / "ack" (receiver) for completed chunks ------

@@ -31,7 +31,7 @@ def set_all(g, param, value):
 def allreduce(g, args):
     n = g.world_size
     factor = 2 * (n - 1) / n
-    sizes = [16 * MiB, 64 * MiB, 256 * MiB] if args.quick else [8 * MiB, 16 * MiB, 32 * MiB, 64 * MiB, 128 * MiB, 256 * MiB, 1024 * MiB]
+    sizes = [16 * MiB, 64 * MiB, 256 * MiB] if args.quick else [8 * MiB, 16 * MiB, 32 * MiB, 64 * MiB, 256 * MiB, 1024 * MiB]
     for dtype in (torch.float32,):
         for size in sizes:
             numel = size // 4
@@ -47,18 +47,19 @@ def allreduce(g, args):
             run("staged auto (r01 path)", N.ALGO_AUTO)
             set_all(g, N.PARAM_PIPE_MIN_BYTES, -1)
             variants = [("push", 0)] if n == 2 else []
-            if g.has_multicast:
+            if g.has_multicast and n > 2:
                 variants.append(("nvls", 1))
-            variants.append(("peer", 2))
+            if args.peer:
+                variants.append(("peer", 2))
             for vname, v in variants:
                 set_all(g, N.PARAM_PIPE_VARIANT, v)
-                grid = [(1, 8, 48)] if args.quick else None
-                if grid is None:
-                    if vname == "push":
-                        grid = [(1, 8, 32), (1, 16, 32), (1, 16, 48), (1, 16, 64), (1, 32, 48), (1, 32, 96), (2, 16, 48), (4, 16, 48)]
-                    else:
-                        grid = [(1, 4, 32), (1, 8, 32), (1, 8, 48), (1, 8, 64), (1, 16, 64), (1, 16, 96), (2, 8, 48), (4, 8, 48),
-                                (2, 16, 64)]
+                if vname == "push":
+                    grid = [(1, 16, 32), (1, 16, 48), (1, 16, 64), (1, 32, 48), (1, 32, 64), (1, 32, 96), (2, 16, 48), (2, 32, 64)]
+                else:
+                    grid = [(1, 8, 48), (1, 16, 32), (1, 16, 48), (1, 16, 64), (1, 16, 96), (1, 32, 64), (2, 16, 48), (2, 16, 64),
+                            (4, 16, 64)]
+                if args.quick:
+                    grid = grid[1:4]
                 for chunk_mib, copy, red in grid:
                     set_all(g, N.PARAM_PIPE_CHUNK_BYTES, chunk_mib * MiB)
                     set_all(g, N.PARAM_PIPE_COPY_CTAS, copy)
@@ -117,6 +118,7 @@ def main():
     ap.add_argument("--world", type=int, default=2)
     ap.add_argument("--what", default="allreduce,sendrecv")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--peer", action="store_true", help="also sweep the peer ld/st pipeline")
     args = ap.parse_args()
     g = LocalGroup(args.world, timeout_ms=20000, staging_bytes=256 << 20, inbox_bytes=32 << 20)
     print(f"# world={args.world} devices={g.devices} shared={g.shared_gpu} multicast={g.has_multicast}", flush=True)
