@@ -227,10 +227,11 @@ typedef enum {
   B200_PARAM_PIPE_CHUNK_BYTES = 5,  /* pipeline chunk size (default 1 MiB; rounded up to 1 MiB multiples) */
   B200_PARAM_PIPE_COPY_CTAS = 6,    /* CTAs per TMA copy role (power of two; default 8, push 16) */
   B200_PARAM_PIPE_RED_CTAS = 7,     /* CTAs of the reduce role (default 48) */
-  B200_PARAM_PIPE_VARIANT = 8,      /* B200_ALGO_PIPE only: force 0 = push, 1 = NVLS roles, 2 = peer ld/st roles */
+  B200_PARAM_PIPE_VARIANT = 8,      /* B200_ALGO_PIPE only: force 0 = push, 1 = NVLS roles, 2 = peer ld/st roles, 3 = pull (2 ranks) */
   B200_PARAM_GRAD_LOCAL_UNROLL = 9, /* world 1 gradient kernel: 16-byte wire units per thread (1, 2, 4, 8) */
   B200_PARAM_P2P_BULK_MIN_CHUNK = 10, /* send/recv: chunks from this size on move with the TMA bulk-copy kernel (0 = never; default 32 KiB) */
-  B200_PARAM_COUNT = 11
+  B200_PARAM_BULK_CFG = 11,         /* send: bulk-engine (lookahead, completion lag) flavour, tuning experiments only */
+  B200_PARAM_COUNT = 12
 } b200_param_t;
 int b200_comm_set_param(b200_comm_t comm, int param, long long value);
 

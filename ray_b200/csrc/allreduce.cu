@@ -357,7 +357,7 @@ extern "C" int b200_allreduce(b200_comm_t c, const void *in, void *out, size_t c
   int pipe_variant = -1;
   if (sym_off < 0 && is_aligned16(in) && is_aligned16(out) && (total & 15) == 0 &&
       (algo == B200_ALGO_PIPE || (algo == B200_ALGO_AUTO && total >= pipe_min_bytes(c)))) {
-    if (c->world == 2) pipe_variant = PIPE_PUSH;
+    if (c->world == 2) pipe_variant = PIPE_PULL;
     else if (c->mc_active && nvls_capable(dtype, op)) pipe_variant = PIPE_NVLS;
     else if (algo == B200_ALGO_PIPE) pipe_variant = PIPE_PEER;  // AUTO without NVLS keeps the two-shot kernel
     if (algo == B200_ALGO_PIPE && c->params[B200_PARAM_PIPE_VARIANT] >= 0)

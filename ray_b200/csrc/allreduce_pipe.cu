@@ -172,6 +172,37 @@ __device__ __forceinline__ void copy_flag_thread(const DevComm &c, const PipeGeo
   }
 }
 
+// The copy-in role shared by the pipelined kernels: CTA j of g.G copies its tiles of the caller's
+// tensor into this rank's slot with the bulk-copy unit and publishes flag0[k][rank] per chunk.
+__device__ __forceinline__ void role_copy_in(const DevComm &c, const PipeArgs &a, const PipeGeom &g, size_t off,
+                                             uint32_t ep, char *dyn_smem, uint32_t j) {
+  __shared__ CopyMailbox mb;
+  if (threadIdx.x == 0) {
+    mb.chunks_done = 0;
+    mb.stop = 0;
+  }
+  const BulkRing ring = bulk_ring_init(dyn_smem);
+  const uint32_t nt = tiles_of_cta(g, j);
+  const uint32_t my_chunks = nt ? (nt - 1) / g.m + 1 : 0;
+  if (threadIdx.x == 0) {
+    char *slot = c.data[c.rank] + off;
+    const bool ok = bulk_copy_run<BulkLocal>(
+        ring, nt, [&](uint32_t i) {
+          const size_t o = tile_off(g, j, i);
+          return BulkTileDesc{a.in + o, tile_len(g, o)};
+        },
+        [&](uint32_t i, uint32_t smem, uint32_t bytes) { bulk_s2g(slot + tile_off(g, j, i), smem, bytes); },
+        [&](uint32_t, bool) { return 1; },
+        [&](uint32_t i) {
+          if ((i + 1) % g.m == 0 || i + 1 == nt) mailbox_post(&mb, i / g.m + 1);  // last tile of a chunk
+        },
+        [&](unsigned ev, unsigned arg) { trace_event(c, ev, arg); });
+    if (!ok) mb.stop = 1;
+  } else if (threadIdx.x == 32) {
+    copy_flag_thread(c, g, &mb, my_chunks, ep + 1);
+  }
+}
+
 constexpr int kItemUnroll = 4;
 constexpr size_t kItemUnits = size_t(kThreads) * kItemUnroll;  // 16-byte units per reduce work item
 
@@ -191,33 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
   const int b = blockIdx.x;
 
   if (b < G) {
-    // ---- copy-in -------------------------------------------------------------------------
-    __shared__ CopyMailbox mb;
-    if (threadIdx.x == 0) {
-      mb.chunks_done = 0;
-      mb.stop = 0;
-    }
-    const BulkRing ring = bulk_ring_init(dyn_smem);
-    const uint32_t j = uint32_t(b);
-    const uint32_t nt = tiles_of_cta(g, j);
-    const uint32_t my_chunks = nt ? (nt - 1) / g.m + 1 : 0;
-    if (threadIdx.x == 0) {
-      char *slot = c.data[r] + off;
-      const bool ok = bulk_copy_run<BulkLocal>(
-          ring, nt, [&](uint32_t i) {
-            const size_t o = tile_off(g, j, i);
-            return BulkTileDesc{a.in + o, tile_len(g, o)};
-          },
-          [&](uint32_t i, uint32_t smem, uint32_t bytes) { bulk_s2g(slot + tile_off(g, j, i), smem, bytes); },
-          [&](uint32_t, bool) { return 1; },
-          [&](uint32_t i) {
-            if ((i + 1) % g.m == 0 || i + 1 == nt) mailbox_post(&mb, i / g.m + 1);  // last tile of a chunk
-          },
-          [&](unsigned ev, unsigned arg) { trace_event(c, ev, arg); });
-      if (!ok) mb.stop = 1;
-    } else if (threadIdx.x == 32) {
-      copy_flag_thread(c, g, &mb, my_chunks, ep + 1);
-    }
+    role_copy_in(c, a, g, off, ep, dyn_smem, uint32_t(b));
   } else if (b < G + Gr) {
     // ---- reduce ------------------------------------------------------------------------------
     const int me = b - G;
@@ -439,6 +444,133 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_push_kernel(DevComm c, 
 }
 
 // ---------------------------------------------------------------------------
+// n == 2, pull: copy-in | pull-reduce
+//
+// Measured on B200 (profiles/r02/bulk_bench*.log): bulk LOADS from a peer reach 770 GB/s with 16
+// CTAs and complete on an mbarrier the moment the bytes are in shared memory, while bulk STORES
+// to a peer top out at 705 GB/s and are only known to be complete ~10 us later (wait_group) --
+// a lag the consumer of a push design has to sit out.  So each rank stages its tensor in its OWN
+// slot (local copy, cheap completion) and the PEER pulls it:
+//
+//   copy-in CTAs : user tensor -> own slot (bulk copies)                        -> flag0[k][rank]
+//   pull CTAs    : one thread keeps kPullLookahead bulk loads of the peer's slot in flight into a
+//                  shared-memory ring; all 512 threads wait on the tile's mbarrier and write
+//                  out = rank0 (op) rank1 straight into the caller's tensor (own operand read
+//                  from the caller's tensor), then release the stage on an "empty" mbarrier.
+// ---------------------------------------------------------------------------
+constexpr int kPullLookahead = 4;  // + the tile being consumed = 5 of the 6 ring stages in flight
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(kThreads, 1) allreduce_pull_kernel(DevComm c, PipeArgs a) {
+  extern __shared__ __align__(128) char dyn_smem[];
+  using Tr = Traits<T>;
+  const uint32_t launch = c.st->launch_ctr;
+  const uint32_t ep = launch * 4u;
+  const size_t off = staging_slot_offset(launch, a.staging_bytes);
+  const PipeGeom g = make_geom(a);
+  const int r = c.rank, peer = 1 - c.rank;
+  const int G = int(g.G), Gr = int(gridDim.x) - G;
+  const int b = blockIdx.x;
+
+  if (b < G) {
+    role_copy_in(c, a, g, off, ep, dyn_smem, uint32_t(b));
+  } else {
+    __shared__ int bail;
+    const uint32_t tiles_smem = smem_u32(dyn_smem);
+    const uint32_t full = tiles_smem + kBulkStages * kBulkTile;  // mbarriers: tile landed
+    const uint32_t empty = full + 8 * kBulkStages;               // mbarriers: tile consumed
+    if (threadIdx.x == 0) {
+      bail = 0;
+      for (int s = 0; s < kBulkStages; ++s) {
+        mbar_init(full + 8 * s, 1);
+        mbar_init(empty + 8 * s, kThreads);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t me = uint32_t(b - G);
+    const uint32_t total_tiles = uint32_t((g.S + kBulkTile - 1) / kBulkTile);
+    const uint32_t nt = total_tiles > me ? (total_tiles - 1 - me) / uint32_t(Gr) + 1 : 0;  // tiles me, me+Gr, ...
+    const uint32_t tiles_per_chunk = uint32_t(g.C / kBulkTile);
+    const char *peer_slot = c.data[peer] + off;
+    uint32_t next_load = 0, ready_chunks = 0;
+    for (uint32_t it = 0; it < nt; ++it) {
+      if (threadIdx.x == 0) {
+        // keep the ring full: tiles it .. it + kPullLookahead
+        while (next_load < nt && next_load <= it + uint32_t(kPullLookahead)) {
+          const uint32_t t = me + next_load * uint32_t(Gr);
+          const uint32_t k = t / tiles_per_chunk;
+          if (k >= ready_chunks) {
+            // chunk k staged by the peer (its slot is readable) AND by the local copy-in CTAs (the
+            // caller's tensor may be overwritten in place)
+            const int st = thread_wait_chunk(c, kSigPipe0, k, ep + 1, next_load == it);
+            if (st < 0) bail = 1;
+            if (st <= 0) break;
+            ready_chunks = k + 1;
+            fence_proxy_async();
+          }
+          const uint32_t s = next_load % kBulkStages;
+          if (next_load >= uint32_t(kBulkStages)) {  // stage consumed by everyone?
+            const uint32_t par = (next_load / kBulkStages - 1) & 1u;
+            while (!mbar_try_wait(empty + 8 * s, par)) {
+            }
+          }
+          const size_t o = size_t(t) * kBulkTile;
+          const uint32_t bytes = tile_len(g, o);
+          mbar_expect_tx(full + 8 * s, bytes);
+          bulk_g2s(tiles_smem + s * kBulkTile, peer_slot + o, bytes, full + 8 * s);
+          ++next_load;
+        }
+      }
+      const uint32_t s = it % kBulkStages;
+      const uint32_t par = (it / kBulkStages) & 1u;
+      unsigned spins = 0;
+      bool alive = true;
+      while (!mbar_try_wait(full + 8 * s, par)) {
+        if ((++spins & 0xff) == 0 && *reinterpret_cast<volatile int *>(&bail)) {
+          alive = false;
+          break;
+        }
+      }
+      if (!alive) break;
+      const uint32_t t = me + it * uint32_t(Gr);
+      const size_t o = size_t(t) * kBulkTile;
+      const uint32_t units = tile_len(g, o) >> 4;
+      uint4 mine[kItemUnroll], theirs[kItemUnroll];
+#pragma unroll
+      for (int q = 0; q < kItemUnroll; ++q) {
+        const uint32_t u = threadIdx.x + uint32_t(q) * kThreads;
+        if (u < units) {
+          mine[q] = ld_stream(a.in + o + (size_t(u) << 4));
+          theirs[q] = lds_v4(tiles_smem + s * kBulkTile + (u << 4));
+        }
+      }
+      mbar_arrive(empty + 8 * s);  // this thread is done with the stage
+#pragma unroll
+      for (int q = 0; q < kItemUnroll; ++q) {
+        const uint32_t u = threadIdx.x + uint32_t(q) * kThreads;
+        if (u < units) {
+          typename Tr::Acc acc = Tr::unpack(r == 0 ? mine[q] : theirs[q]);
+          Tr::template reduce<OP>(acc, Tr::unpack(r == 0 ? theirs[q] : mine[q]));  // rank-ascending
+          if (OP == B200_AVG) Tr::average(acc, 2);
+          st_vec(a.out + o + (size_t(u) << 4), Tr::pack(acc));
+        }
+      }
+    }
+  }
+  finish_launch(c);
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 static int pow2_floor(int x) {
@@ -463,7 +595,7 @@ int set_dyn_smem(int device, const void *fn) {
 size_t pipe_max_bytes(const b200_comm *c, int variant) {
   const size_t C = pipe_chunk_bytes(c);
   size_t cap = c->staging_bytes;
-  if (variant == PIPE_PUSH) cap = c->staging_bytes / size_t(c->world - 1);
+  if (variant == PIPE_PUSH) cap = c->staging_bytes / size_t(c->world - 1);  // PIPE_PULL stages in the rank's own slot
   const size_t by_chunks = size_t(kMaxPipeChunks) * C;
   cap = cap < by_chunks ? cap : by_chunks;
   return cap / C * C;  // whole chunks, so a split message continues on a chunk boundary
@@ -482,9 +614,9 @@ int launch_allreduce_pipe(b200_comm *c, const char *in, char *out, size_t nbytes
   PipeArgs a{in, out, nbytes, c->staging_bytes, pipe_chunk_bytes(c), 0};
   const long long pc = c->params[B200_PARAM_PIPE_COPY_CTAS];
   const long long pr = c->params[B200_PARAM_PIPE_RED_CTAS];
-  int G = pc > 0 ? int(pc) : (variant == PIPE_PUSH ? 16 : 8);
-  int Gr = pr > 0 ? int(pr) : 48;
-  const int roles = variant == PIPE_PUSH ? 1 : 2;
+  int G = pc > 0 ? int(pc) : (variant == PIPE_NVLS || variant == PIPE_PEER ? 8 : 16);
+  int Gr = pr > 0 ? int(pr) : (variant == PIPE_PULL ? 24 : 48);
+  const int roles = (variant == PIPE_PUSH || variant == PIPE_PULL) ? 1 : 2;
   int cap = c->forced_blocks > 0 ? c->forced_blocks : c->sm_count;
   if (roles * G + Gr > cap) {  // shared-GPU harness / small parts: shrink, keep at least one reducer
     while (G > 1 && roles * G + 1 > cap / 2) G /= 2;
@@ -499,7 +631,15 @@ int launch_allreduce_pipe(b200_comm *c, const char *in, char *out, size_t nbytes
   const int grid = roles * G + Gr;
   DevComm dc = c->dev();
   int rc = B200_OK;
-  if (variant == PIPE_PUSH) {
+  if (variant == PIPE_PULL) {
+    if (c->world != 2) {
+      set_error("the pull all-reduce is a 2-rank kernel");
+      return B200_ERR_UNSUPPORTED;
+    }
+    auto k = allreduce_pull_kernel<T, OP>;
+    if ((rc = set_dyn_smem(c->device, reinterpret_cast<const void *>(k)))) return rc;
+    k<<<grid, kThreads, kBulkSmemBytes, stream>>>(dc, a);
+  } else if (variant == PIPE_PUSH) {
     auto k = allreduce_push_kernel<T, OP>;
     if ((rc = set_dyn_smem(c->device, reinterpret_cast<const void *>(k)))) return rc;
     k<<<grid, kThreads, kBulkSmemBytes, stream>>>(dc, a);

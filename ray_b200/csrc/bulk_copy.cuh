@@ -38,6 +38,10 @@ struct BulkLocal {
 struct BulkRemote {
   static constexpr int kLookahead = kBulkLookaheadRemote, kLag = kBulkLagRemote;
 };
+template <int LA, int LAG>
+struct BulkCfg {  // experiments (B200_PARAM_BULK_CFG)
+  static constexpr int kLookahead = LA, kLag = LAG;
+};
 constexpr size_t kBulkSmemBytes = size_t(kBulkStages) * kBulkTile + 16 * kBulkStages;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

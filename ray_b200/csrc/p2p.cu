@@ -37,6 +37,7 @@ struct P2PArgs {
   size_t nbytes;
   size_t chunk;  // bytes per chunk of THIS message (<= slot size), same on both sides
   int peer;
+  int cfg;       // bulk-engine flavour of the sender (B200_PARAM_BULK_CFG; tuning experiments)
 };
 
 // Chunk size is a pure function of the message size, so sender and receiver agree: big messages
@@ -211,7 +212,15 @@ __global__ void __launch_bounds__(kThreads, 1) p2p_bulk_kernel(DevComm c, P2PArg
           });
     };
     // the sender's stores cross NVLink (long completion latency), the receiver's stay in local HBM
-    const bool ok = SEND ? run(BulkRemote{}) : run(BulkLocal{});
+    bool ok;
+    if (!SEND) ok = run(BulkLocal{});
+    else if (a.cfg == 1) ok = run(BulkCfg<3, 10>{});
+    else if (a.cfg == 2) ok = run(BulkCfg<3, 16>{});
+    else if (a.cfg == 3) ok = run(BulkCfg<5, 16>{});
+    else if (a.cfg == 4) ok = run(BulkCfg<5, 24>{});
+    else if (a.cfg == 5) ok = run(BulkCfg<4, 16>{});
+    else if (a.cfg == 6) ok = run(BulkCfg<3, 24>{});
+    else ok = run(BulkRemote{});
     if (!ok) stop = 1;
   } else if (threadIdx.x == 32 && nq > 0) {
     // ---- flag thread: publishes "ready" (sender) / "ack" (receiver) for completed chunks ------
@@ -258,7 +267,7 @@ static int p2p_common(b200_comm *c, void *buf, size_t nbytes, int peer, cudaStre
   const size_t nchunks = (nbytes + chunk - 1) / chunk;
   // Grid is a pure function of the message size so both sides pair CTA b with CTA b.
   int g = int(nchunks < size_t(kP2PRings) ? nchunks : size_t(kP2PRings));
-  P2PArgs a{static_cast<char *>(buf), nbytes, chunk, peer};
+  P2PArgs a{static_cast<char *>(buf), nbytes, chunk, peer, int(c->params[B200_PARAM_BULK_CFG])};
   // The protocol (rings, slots, chunking) is a function of the message size alone; HOW this side
   // moves its bytes is a local choice: the bulk-copy unit when the tensor is 16-byte aligned, a
   // whole number of 16-byte units and the chunks are big enough to be worth a TMA pipeline.

@@ -114,6 +114,28 @@ int main() {
       CK(cudaDeviceEnablePeerAccess(1, 0));
     }
   }
+  if (rdst) {
+    // pull direction: source on the PEER, destination local
+    for (int ctas : {1, 8, 16, 32}) {
+      run<6, 3, 1>("rload", rdst, dst, ctas, 32 << 10, 1, total);   // TMA loads only, from the peer
+      run<6, 5, 1>("rload", rdst, dst, ctas, 32 << 10, 1, total);
+      run<12, 11, 1>("rload", rdst, dst, ctas, 16 << 10, 1, total);
+      run<6, 3, 1>("rpull", rdst, dst, ctas, 32 << 10, 0, total);   // peer -> smem -> local HBM
+      run<6, 5, 1>("rpull", rdst, dst, ctas, 32 << 10, 0, total);
+    }
+    for (int ctas : {8, 16, 32, 64, 148}) {
+      cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+      float best = 1e9;
+      for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(a));
+        ldst_kernel<<<ctas, 512>>>((const uint4 *)rdst, (uint4 *)dst, total / 16);
+        CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b));
+        if (rep && ms < best) best = ms;
+      }
+      printf("rpull    ld/st 512thr x8  ctas=%3d : %8.1f us  %7.1f GB/s (%.1f per CTA)\n", ctas, best * 1e3, total / 1e9 / (best * 1e-3), total / 1e9 / (best * 1e-3) / ctas);
+    }
+  }
   for (int remote = 0; remote < (rdst ? 2 : 1); ++remote) {
     char *d = remote ? rdst : dst;
     const char *nm = remote ? "remote" : "local";
@@ -123,13 +145,8 @@ int main() {
         run<6, 3, 1>(nm, src, d, ctas, 32 << 10, mode, total);
       }
       run<6, 5, 1>(nm, src, d, ctas, 32 << 10, 0, total);
-      run<12, 8, 1>(nm, src, d, ctas, 16 << 10, 0, total);
-      run<3, 2, 1>(nm, src, d, ctas, 64 << 10, 0, total);
-      run<24, 16, 1>(nm, src, d, ctas, 8 << 10, 0, total);
+      run<6, 4, 1>(nm, src, d, ctas, 32 << 10, 0, total);
       run<3, 2, 2>(nm, src, d, ctas, 32 << 10, 0, total);
-      run<3, 2, 4>(nm, src, d, ctas, 16 << 10, 0, total);
-      run<6, 4, 4>(nm, src, d, ctas, 8 << 10, 0, total);
-      run<3, 2, 8>(nm, src, d, ctas, 8 << 10, 0, total);
     }
     for (int ctas : {8, 16, 32, 64, 148}) {
       cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));

@@ -46,14 +46,16 @@ def allreduce(g, args):
             set_all(g, N.PARAM_PIPE_MIN_BYTES, 1 << 40)  # AUTO without the pipeline = round-1 behaviour
             run("staged auto (r01 path)", N.ALGO_AUTO)
             set_all(g, N.PARAM_PIPE_MIN_BYTES, -1)
-            variants = [("push", 0)] if n == 2 else []
+            variants = [("pull", 3)] + ([("push", 0)] if args.push else []) if n == 2 else []
             if g.has_multicast and n > 2:
                 variants.append(("nvls", 1))
             if args.peer:
                 variants.append(("peer", 2))
             for vname, v in variants:
                 set_all(g, N.PARAM_PIPE_VARIANT, v)
-                if vname == "push":
+                if vname == "pull":
+                    grid = [(1, 8, 24), (1, 16, 16), (1, 16, 24), (1, 16, 32), (1, 16, 48), (1, 32, 24), (1, 32, 32), (2, 16, 24)]
+                elif vname == "push":
                     grid = [(1, 16, 32), (1, 16, 48), (1, 16, 64), (1, 32, 48), (1, 32, 64), (1, 32, 96), (2, 16, 48), (2, 32, 64)]
                 else:
                     grid = [(1, 8, 48), (1, 16, 32), (1, 16, 48), (1, 16, 64), (1, 16, 96), (1, 32, 64), (2, 16, 48), (2, 16, 64),
@@ -78,12 +80,16 @@ def sendrecv(g, args):
         xs = [torch.ones(size // 4, device=g.device(r)) for r in range(n)]
         iters = 20 if size <= 64 * MiB else 6
         call = lambda c, r: (c.send(xs[0], 1) if r == 0 else (c.recv(xs[1], 0) if r == 1 else None))  # noqa: E731
-        for label, v in (("ld/st", 0), ("bulk", -1)):
+        for label, v, cfg in (("ld/st", 0, -1), ("bulk", -1, -1), ("bulk la3 lag10", -1, 1), ("bulk la3 lag16", -1, 2),
+                              ("bulk la5 lag16", -1, 3), ("bulk la5 lag24", -1, 4), ("bulk la4 lag16", -1, 5),
+                              ("bulk la3 lag24", -1, 6)):
             set_all(g, N.PARAM_P2P_BULK_MIN_CHUNK, v)
+            set_all(g, N.PARAM_BULK_CFG, cfg)
             us = time_graphs(g, call, iters)
-            print(f"sendrecv n={n} {size / MiB:8.2f} MiB {label:8s} {us:9.1f} us  {size / us / 1e3:7.1f} GB/s", flush=True)
+            print(f"sendrecv n={n} {size / MiB:8.2f} MiB {label:16s} {us:9.1f} us  {size / us / 1e3:7.1f} GB/s", flush=True)
         del xs
     set_all(g, N.PARAM_P2P_BULK_MIN_CHUNK, -1)
+    set_all(g, N.PARAM_BULK_CFG, -1)
 
 
 def gradlocal(g, args):
@@ -119,6 +125,7 @@ def main():
     ap.add_argument("--what", default="allreduce,sendrecv")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--peer", action="store_true", help="also sweep the peer ld/st pipeline")
+    ap.add_argument("--push", action="store_true", help="also sweep the 2-rank push kernel")
     args = ap.parse_args()
     g = LocalGroup(args.world, timeout_ms=20000, staging_bytes=256 << 20, inbox_bytes=32 << 20)
     print(f"# world={args.world} devices={g.devices} shared={g.shared_gpu} multicast={g.has_multicast}", flush=True)

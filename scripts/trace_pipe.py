@@ -22,7 +22,7 @@ ap.add_argument("--red", type=int, default=-1)
 ap.add_argument("--chunk", type=int, default=-1)
 ap.add_argument("--ctas", default="0,1,16,17")
 args = ap.parse_args()
-V = {"push": 0, "nvls": 1, "peer": 2}[args.variant]
+V = {"push": 0, "nvls": 1, "peer": 2, "pull": 3}[args.variant]
 g = LocalGroup(args.world, timeout_ms=10000, staging_bytes=256 << 20, inbox_bytes=8 << 20)
 for c in g.comms:
     c.set_param(N.PARAM_PIPE_VARIANT, V)

@@ -40,6 +40,8 @@ def _variants(g, world):
     out = [("peer", 2)]
     if (world - 1) * max(SIZES) <= (40 << 20):
         out.append(("push", 0))
+    if world == 2:
+        out.append(("pull", 3))
     if g.has_multicast:
         out.append(("nvls", 1))
     return out, N
