@@ -44,9 +44,9 @@ struct PipeArgs {
 
 struct PipeGeom {
   size_t S, C;
-  uint32_t K;  // chunks
-  uint32_t G;  // copy CTAs per role
-  uint32_t m;  // tiles per copy CTA per full chunk
+  uint32_t K;      // chunks
+  uint32_t G;      // copy CTAs per role
+  uint32_t share;  // bytes of a full chunk each copy CTA moves: C / G (a multiple of kBulkTile)
 };
 __device__ __forceinline__ PipeGeom make_geom(const PipeArgs &a) {
   PipeGeom g;
@@ -54,32 +54,31 @@ __device__ __forceinline__ PipeGeom make_geom(const PipeArgs &a) {
   g.C = a.chunk_bytes;
   g.K = uint32_t((g.S + g.C - 1) / g.C);
   g.G = uint32_t(a.copy_ctas);
-  g.m = uint32_t(g.C / (size_t(g.G) * kBulkTile));
+  g.share = uint32_t(g.C / g.G);
   return g;
 }
 __device__ __forceinline__ size_t chunk_len(const PipeGeom &g, uint32_t k) {
   const size_t lo = size_t(k) * g.C;
   return (g.S - lo) < g.C ? (g.S - lo) : g.C;
 }
-// byte offset of the i-th tile of copy CTA j (tiles past the end of the message are never asked for)
-__device__ __forceinline__ size_t tile_off(const PipeGeom &g, uint32_t j, uint32_t i) {
-  const uint32_t k = i / g.m, t = (i - k * g.m) * g.G + j;
-  return size_t(k) * g.C + size_t(t) * kBulkTile;
+// Copy CTA j moves bytes [j*share, (j+1)*share) of every chunk (clipped by the message end).
+__device__ __forceinline__ size_t share_off(const PipeGeom &g, uint32_t j, uint32_t k) {
+  return size_t(k) * g.C + size_t(j) * g.share;
 }
-__device__ __forceinline__ uint32_t tile_len(const PipeGeom &g, size_t off) {
-  return uint32_t((g.S - off) < size_t(kBulkTile) ? (g.S - off) : size_t(kBulkTile));
+__device__ __forceinline__ uint32_t share_len(const PipeGeom &g, uint32_t j, uint32_t k) {
+  const size_t len = chunk_len(g, k), lo = size_t(j) * g.share;
+  if (lo >= len) return 0;
+  return uint32_t((len - lo) < size_t(g.share) ? (len - lo) : size_t(g.share));
 }
-__device__ __forceinline__ uint32_t tiles_of_cta(const PipeGeom &g, uint32_t j) {
-  const size_t full = g.S / g.C, rem = g.S - full * g.C;
-  uint32_t nt = uint32_t(full) * g.m;
-  for (uint32_t q = 0; q < g.m; ++q)
-    if ((size_t(q) * g.G + size_t(j)) * kBulkTile < rem) ++nt;
-  return nt;
+// chunks in which copy CTA j has bytes: all full chunks, plus the ragged last one if it reaches j's share
+__device__ __forceinline__ uint32_t chunks_of_cta(const PipeGeom &g, uint32_t j) {
+  if (g.K == 0) return 0;
+  return share_len(g, j, g.K - 1) ? g.K : g.K - 1;
 }
-// copy CTAs that own at least one tile of chunk k (= arrivals expected on its counter)
+// copy CTAs that own bytes of chunk k (= arrivals expected on its counter)
 __device__ __forceinline__ uint32_t copy_arrivals(const PipeGeom &g, uint32_t k) {
-  const size_t tiles = (chunk_len(g, k) + kBulkTile - 1) / kBulkTile;
-  return uint32_t(tiles < size_t(g.G) ? tiles : size_t(g.G));
+  const size_t pieces = (chunk_len(g, k) + g.share - 1) / g.share;
+  return uint32_t(pieces < size_t(g.G) ? pieces : size_t(g.G));
 }
 
 // Copy CTAs split the work between two threads: thread 0 drives the bulk-copy unit and only
@@ -182,21 +181,16 @@ __device__ __forceinline__ void role_copy_in(const DevComm &c, const PipeArgs &a
     mb.stop = 0;
   }
   const BulkRing ring = bulk_ring_init(dyn_smem);
-  const uint32_t nt = tiles_of_cta(g, j);
-  const uint32_t my_chunks = nt ? (nt - 1) / g.m + 1 : 0;
+  const uint32_t my_chunks = chunks_of_cta(g, j);
   if (threadIdx.x == 0) {
     char *slot = c.data[c.rank] + off;
-    const bool ok = bulk_copy_run<BulkLocal>(
-        ring, nt, [&](uint32_t i) {
-          const size_t o = tile_off(g, j, i);
-          return BulkTileDesc{a.in + o, tile_len(g, o)};
+    const bool ok = bulk_copy_segments<BulkLocal>(
+        ring, my_chunks,
+        [&](uint32_t k) {
+          const size_t o = share_off(g, j, k);
+          return BulkSeg{a.in + o, slot + o, share_len(g, j, k)};
         },
-        [&](uint32_t i, uint32_t smem, uint32_t bytes) { bulk_s2g(slot + tile_off(g, j, i), smem, bytes); },
-        [&](uint32_t, bool) { return 1; },
-        [&](uint32_t i) {
-          if ((i + 1) % g.m == 0 || i + 1 == nt) mailbox_post(&mb, i / g.m + 1);  // last tile of a chunk
-        },
-        [&](unsigned ev, unsigned arg) { trace_event(c, ev, arg); });
+        [&](uint32_t, bool) { return 1; }, [&](uint32_t k) { mailbox_post(&mb, k + 1); });
     if (!ok) mb.stop = 1;
   } else if (threadIdx.x == 32) {
     copy_flag_thread(c, g, &mb, my_chunks, ep + 1);
@@ -302,33 +296,26 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
     const BulkRing ring = bulk_ring_init(dyn_smem);
     if (threadIdx.x == 0) {
       const uint32_t j = uint32_t(b - G - Gr);
-      const uint32_t nt = tiles_of_cta(g, j);
       const char *slot = c.data[r] + off;
-      uint32_t ready = 0;  // chunks [0, ready) are published by every rank
-      bulk_copy_run<BulkLocal>(
-          ring, nt, [&](uint32_t i) {
-            const size_t o = tile_off(g, j, i);
-            return BulkTileDesc{slot + o, tile_len(g, o)};
+      bulk_copy_segments<BulkLocal>(
+          ring, chunks_of_cta(g, j),
+          [&](uint32_t k) {
+            const size_t o = share_off(g, j, k);
+            return BulkSeg{slot + o, a.out + o, share_len(g, j, k)};
           },
-          [&](uint32_t i, uint32_t smem, uint32_t bytes) { bulk_s2g(a.out + tile_off(g, j, i), smem, bytes); },
-          [&](uint32_t i, bool block) {
-            const uint32_t k = i / g.m;
-            if (k < ready) return 1;
+          [&](uint32_t k, bool block) {
             const int st = thread_wait_chunk(c, kSigPipe1, k, ep + 2, block);
-            if (st == 1) {
-              ready = k + 1;
-              fence_proxy_async();  // peers' stores (generic proxy) before our bulk reads (async proxy)
-            }
+            if (st == 1) fence_proxy_async();  // peers' stores (generic proxy) before our bulk reads (async proxy)
             return st;
           },
-          [&](uint32_t) {}, [&](unsigned ev, unsigned arg) { trace_event(c, 40 + ev, arg); });
+          [&](uint32_t) {});
     }
   }
   finish_launch(c);
 }
 
 // ---------------------------------------------------------------------------
-// one-shot push (selected for n == 2; correct for any n with (n-1)*S <= slot)
+// one-shot push, n == 2 (kept for comparison with the pull kernel below, which replaced it as the default)
 // ---------------------------------------------------------------------------
 template <typename T, int OP, int UNR, int NW>  // NW: compile-time bound on the world size
 __device__ __forceinline__ void push_reduce_item(const DevComm &c, const PipeArgs &a, size_t sub, size_t off,
@@ -375,10 +362,10 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_push_kernel(DevComm c, 
   const int n = c.world, r = c.rank;
   const int G = int(g.G), Gr = int(gridDim.x) - G;
   const int b = blockIdx.x;
-  const size_t sub = g.S;  // bytes per source sub-slot (S is a multiple of 16)
+  const size_t sub = g.S;  // the peer's data starts at the slot base (2 ranks: one sub-slot)
 
   if (b < G) {
-    // ---- push: my tensor into every peer's slot, sub-slot "me" ------------------------------
+    // ---- push: my tensor into the peer's slot ---------------------------------------------------
     __shared__ CopyMailbox mb;
     if (threadIdx.x == 0) {
       mb.chunks_done = 0;
@@ -386,27 +373,16 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_push_kernel(DevComm c, 
     }
     const BulkRing ring = bulk_ring_init(dyn_smem);
     const uint32_t j = uint32_t(b);
-    const uint32_t nt = tiles_of_cta(g, j);
-    const uint32_t my_chunks = nt ? (nt - 1) / g.m + 1 : 0;
+    const uint32_t my_chunks = chunks_of_cta(g, j);
     if (threadIdx.x == 0) {
-      const bool ok = bulk_copy_run<BulkRemote>(
-          ring, nt, [&](uint32_t i) {
-            const size_t o = tile_off(g, j, i);
-            return BulkTileDesc{a.in + o, tile_len(g, o)};
+      char *peer_slot = c.data[1 - r] + off;
+      const bool ok = bulk_copy_segments<BulkRemote>(
+          ring, my_chunks,
+          [&](uint32_t k) {
+            const size_t o = share_off(g, j, k);
+            return BulkSeg{a.in + o, peer_slot + o, share_len(g, j, k)};
           },
-          [&](uint32_t i, uint32_t smem, uint32_t bytes) {
-            const size_t o = tile_off(g, j, i);
-            for (int q = 1; q < n; ++q) {
-              int p = r + q;
-              if (p >= n) p -= n;
-              bulk_s2g(c.data[p] + off + size_t(r < p ? r : r - 1) * sub + o, smem, bytes);
-            }
-          },
-          [&](uint32_t, bool) { return 1; },
-          [&](uint32_t i) {
-            if ((i + 1) % g.m == 0 || i + 1 == nt) mailbox_post(&mb, i / g.m + 1);
-          },
-          [&](unsigned ev, unsigned arg) { trace_event(c, ev, arg); });
+          [&](uint32_t, bool) { return 1; }, [&](uint32_t k) { mailbox_post(&mb, k + 1); });
       if (!ok) mb.stop = 1;
     } else if (threadIdx.x == 32) {
       copy_flag_thread(c, g, &mb, my_chunks, ep + 1);
@@ -454,11 +430,13 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_push_kernel(DevComm c, 
 //
 //   copy-in CTAs : user tensor -> own slot (bulk copies)                        -> flag0[k][rank]
 //   pull CTAs    : one thread keeps kPullLookahead bulk loads of the peer's slot in flight into a
-//                  shared-memory ring; all 512 threads wait on the tile's mbarrier and write
-//                  out = rank0 (op) rank1 straight into the caller's tensor (own operand read
-//                  from the caller's tensor), then release the stage on an "empty" mbarrier.
+//                  shared-memory ring (plus a bulk load of the matching piece of the caller's
+//                  tensor); all 512 threads wait on the tile's mbarrier and write
+//                  out = rank0 (op) rank1 straight into the caller's tensor, then release the
+//                  stage on an "empty" mbarrier.
 // ---------------------------------------------------------------------------
 constexpr int kPullLookahead = 4;  // + the tile being consumed = 5 of the 6 ring stages in flight
+constexpr int kPullTile = kBulkTile / 2;  // payload bytes per tile (a stage holds both operands)
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -497,10 +475,13 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pull_kernel(DevComm c, 
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // A ring stage holds BOTH operands of one tile: [peer's kPullTile bytes | own kPullTile bytes],
+    // each fetched by its own bulk load (remote slot / local caller tensor) onto the same mbarrier,
+    // so the 512 consumer threads never wait on a global-memory load of their own.
     const uint32_t me = uint32_t(b - G);
-    const uint32_t total_tiles = uint32_t((g.S + kBulkTile - 1) / kBulkTile);
+    const uint32_t total_tiles = uint32_t((g.S + kPullTile - 1) / kPullTile);
     const uint32_t nt = total_tiles > me ? (total_tiles - 1 - me) / uint32_t(Gr) + 1 : 0;  // tiles me, me+Gr, ...
-    const uint32_t tiles_per_chunk = uint32_t(g.C / kBulkTile);
+    const uint32_t tiles_per_chunk = uint32_t(g.C / kPullTile);
     const char *peer_slot = c.data[peer] + off;
     uint32_t next_load = 0, ready_chunks = 0;
     for (uint32_t it = 0; it < nt; ++it) {
@@ -512,11 +493,13 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pull_kernel(DevComm c, 
           if (k >= ready_chunks) {
             // chunk k staged by the peer (its slot is readable) AND by the local copy-in CTAs (the
             // caller's tensor may be overwritten in place)
+            if (next_load == it) trace_event(c, 31, k);
             const int st = thread_wait_chunk(c, kSigPipe0, k, ep + 1, next_load == it);
             if (st < 0) bail = 1;
             if (st <= 0) break;
             ready_chunks = k + 1;
             fence_proxy_async();
+            trace_event(c, 32, k);
           }
           const uint32_t s = next_load % kBulkStages;
           if (next_load >= uint32_t(kBulkStages)) {  // stage consumed by everyone?
@@ -524,10 +507,12 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pull_kernel(DevComm c, 
             while (!mbar_try_wait(empty + 8 * s, par)) {
             }
           }
-          const size_t o = size_t(t) * kBulkTile;
-          const uint32_t bytes = tile_len(g, o);
-          mbar_expect_tx(full + 8 * s, bytes);
+          const size_t o = size_t(t) * kPullTile;
+          const uint32_t bytes = uint32_t((g.S - o) < size_t(kPullTile) ? (g.S - o) : size_t(kPullTile));
+          mbar_expect_tx(full + 8 * s, 2 * bytes);
           bulk_g2s(tiles_smem + s * kBulkTile, peer_slot + o, bytes, full + 8 * s);
+          bulk_g2s(tiles_smem + s * kBulkTile + kPullTile, a.in + o, bytes, full + 8 * s);
+          trace_event(c, 30, next_load);
           ++next_load;
         }
       }
@@ -542,21 +527,23 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pull_kernel(DevComm c, 
         }
       }
       if (!alive) break;
+      if (threadIdx.x == 0) trace_event(c, 33, it);
       const uint32_t t = me + it * uint32_t(Gr);
-      const size_t o = size_t(t) * kBulkTile;
-      const uint32_t units = tile_len(g, o) >> 4;
-      uint4 mine[kItemUnroll], theirs[kItemUnroll];
+      const size_t o = size_t(t) * kPullTile;
+      const uint32_t units = uint32_t(((g.S - o) < size_t(kPullTile) ? (g.S - o) : size_t(kPullTile)) >> 4);
+      constexpr int kPerThread = kPullTile / 16 / kThreads;
+      uint4 mine[kPerThread], theirs[kPerThread];
 #pragma unroll
-      for (int q = 0; q < kItemUnroll; ++q) {
+      for (int q = 0; q < kPerThread; ++q) {
         const uint32_t u = threadIdx.x + uint32_t(q) * kThreads;
         if (u < units) {
-          mine[q] = ld_stream(a.in + o + (size_t(u) << 4));
           theirs[q] = lds_v4(tiles_smem + s * kBulkTile + (u << 4));
+          mine[q] = lds_v4(tiles_smem + s * kBulkTile + kPullTile + (u << 4));
         }
       }
       mbar_arrive(empty + 8 * s);  // this thread is done with the stage
 #pragma unroll
-      for (int q = 0; q < kItemUnroll; ++q) {
+      for (int q = 0; q < kPerThread; ++q) {
         const uint32_t u = threadIdx.x + uint32_t(q) * kThreads;
         if (u < units) {
           typename Tr::Acc acc = Tr::unpack(r == 0 ? mine[q] : theirs[q]);
@@ -595,7 +582,6 @@ int set_dyn_smem(int device, const void *fn) {
 size_t pipe_max_bytes(const b200_comm *c, int variant) {
   const size_t C = pipe_chunk_bytes(c);
   size_t cap = c->staging_bytes;
-  if (variant == PIPE_PUSH) cap = c->staging_bytes / size_t(c->world - 1);  // PIPE_PULL stages in the rank's own slot
   const size_t by_chunks = size_t(kMaxPipeChunks) * C;
   cap = cap < by_chunks ? cap : by_chunks;
   return cap / C * C;  // whole chunks, so a split message continues on a chunk boundary
@@ -604,7 +590,7 @@ size_t pipe_max_bytes(const b200_comm *c, int variant) {
 size_t pipe_chunk_bytes(const b200_comm *c) {
   const long long v = c->params[B200_PARAM_PIPE_CHUNK_BYTES];
   size_t C = v > 0 ? size_t(v) : (size_t(1) << 20);
-  const size_t quantum = size_t(32) * kBulkTile;  // any power-of-two copy-CTA count up to 32 divides it
+  const size_t quantum = size_t(32) * kBulkTile;  // C / G is a whole number of tiles for any power-of-two G <= 32
   return round_up(C, quantum);
 }
 
@@ -615,7 +601,7 @@ int launch_allreduce_pipe(b200_comm *c, const char *in, char *out, size_t nbytes
   const long long pc = c->params[B200_PARAM_PIPE_COPY_CTAS];
   const long long pr = c->params[B200_PARAM_PIPE_RED_CTAS];
   int G = pc > 0 ? int(pc) : (variant == PIPE_NVLS || variant == PIPE_PEER ? 8 : 16);
-  int Gr = pr > 0 ? int(pr) : (variant == PIPE_PULL ? 24 : 48);
+  int Gr = pr > 0 ? int(pr) : (variant == PIPE_PULL ? 32 : 48);
   const int roles = (variant == PIPE_PUSH || variant == PIPE_PULL) ? 1 : 2;
   int cap = c->forced_blocks > 0 ? c->forced_blocks : c->sm_count;
   if (roles * G + Gr > cap) {  // shared-GPU harness / small parts: shrink, keep at least one reducer
@@ -640,6 +626,10 @@ int launch_allreduce_pipe(b200_comm *c, const char *in, char *out, size_t nbytes
     if ((rc = set_dyn_smem(c->device, reinterpret_cast<const void *>(k)))) return rc;
     k<<<grid, kThreads, kBulkSmemBytes, stream>>>(dc, a);
   } else if (variant == PIPE_PUSH) {
+    if (c->world != 2) {
+      set_error("the push all-reduce is a 2-rank kernel");
+      return B200_ERR_UNSUPPORTED;
+    }
     auto k = allreduce_push_kernel<T, OP>;
     if ((rc = set_dyn_smem(c->device, reinterpret_cast<const void *>(k)))) return rc;
     k<<<grid, kThreads, kBulkSmemBytes, stream>>>(dc, a);

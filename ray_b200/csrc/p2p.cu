@@ -37,7 +37,6 @@ struct P2PArgs {
   size_t nbytes;
   size_t chunk;  // bytes per chunk of THIS message (<= slot size), same on both sides
   int peer;
-  int cfg;       // bulk-engine flavour of the sender (B200_PARAM_BULK_CFG; tuning experiments)
 };
 
 // Chunk size is a pure function of the message size, so sender and receiver agree: big messages
@@ -161,66 +160,35 @@ __global__ void __launch_bounds__(kThreads, 1) p2p_bulk_kernel(DevComm c, P2PArg
   }
   const BulkRing br = bulk_ring_init(dyn_smem);  // contains the __syncthreads
 
-  const uint32_t tpc = uint32_t((chunk + kBulkTile - 1) / kBulkTile);  // tiles of a full chunk
   const uint32_t nq32 = uint32_t(nq);
-  auto chunk_lo = [&](uint32_t q) { return (size_t(b) + size_t(q) * size_t(G)) * chunk; };
-  auto chunk_len = [&](uint32_t q) {
-    const size_t lo = chunk_lo(q);
-    return (a.nbytes - lo) < chunk ? (a.nbytes - lo) : chunk;
-  };
   if (threadIdx.x == 0 && nq > 0) {
-    // ---- copy thread ---------------------------------------------------------------------
-    const uint32_t last_tiles = uint32_t((chunk_len(nq32 - 1) + kBulkTile - 1) / kBulkTile);
-    const uint32_t nt = (nq32 - 1) * tpc + last_tiles;
-    uint32_t gated = 0;  // chunks [0, gated) passed their gate
-    auto slot_of = [&](uint32_t q) { return ring + size_t((seq0 + q) % kP2PSlots) * slot_bytes; };
-    auto run = [&](auto lag) {
-      return bulk_copy_run<decltype(lag)>(
-          br, nt,
-          [&](uint32_t i) {
-            const uint32_t q = i / tpc, t = i - q * tpc;
-            const size_t len = chunk_len(q), o = size_t(t) * kBulkTile;
-            const uint32_t bytes = uint32_t((len - o) < size_t(kBulkTile) ? (len - o) : size_t(kBulkTile));
-            return BulkTileDesc{SEND ? a.buf + chunk_lo(q) + o : slot_of(q) + o, bytes};
-          },
-          [&](uint32_t i, uint32_t smem, uint32_t bytes) {
-            const uint32_t q = i / tpc;
-            const size_t o = size_t(i - q * tpc) * kBulkTile;
-            bulk_s2g(SEND ? slot_of(q) + o : a.buf + chunk_lo(q) + o, smem, bytes);
-          },
-          [&](uint32_t i, bool block) {
-            const uint32_t q = i / tpc;
-            if (q < gated) return 1;
-            const uint32_t seq = seq0 + q;
-            // sender: the slot was consumed (ack in MY pad); receiver: the chunk landed (ready in MY pad)
-            const uint32_t *flag = SEND ? ack : ready + seq % kP2PSlots;
-            const uint32_t target = SEND ? seq + 1u - kP2PSlots : seq + 1u;
-            if (block) {
-              if (!wait_flag_ge(c, flag, target)) return -1;
-            } else if (int32_t(ld_acquire_sys(flag) - target) < 0) {
-              return 0;
-            }
-            if (!SEND) fence_proxy_async();  // the peer's stores before our bulk reads
-            gated = q + 1;
-            return 1;
-          },
-          [&](uint32_t i) {
-            if ((i + 1) % tpc == 0 || i + 1 == nt) {  // last tile of a chunk
-              __threadfence_block();
-              mailbox = i / tpc + 1;
-            }
-          });
+    // ---- copy thread: one segment per chunk ---------------------------------------------------
+    auto seg = [&](uint32_t q) {
+      const size_t lo = (size_t(b) + size_t(q) * size_t(G)) * chunk;
+      const uint32_t len = uint32_t((a.nbytes - lo) < chunk ? (a.nbytes - lo) : chunk);
+      char *slot = ring + size_t((seq0 + q) % kP2PSlots) * slot_bytes;
+      return SEND ? BulkSeg{a.buf + lo, slot, len} : BulkSeg{slot, a.buf + lo, len};
     };
-    // the sender's stores cross NVLink (long completion latency), the receiver's stay in local HBM
-    bool ok;
-    if (!SEND) ok = run(BulkLocal{});
-    else if (a.cfg == 1) ok = run(BulkCfg<3, 10>{});
-    else if (a.cfg == 2) ok = run(BulkCfg<3, 16>{});
-    else if (a.cfg == 3) ok = run(BulkCfg<5, 16>{});
-    else if (a.cfg == 4) ok = run(BulkCfg<5, 24>{});
-    else if (a.cfg == 5) ok = run(BulkCfg<4, 16>{});
-    else if (a.cfg == 6) ok = run(BulkCfg<3, 24>{});
-    else ok = run(BulkRemote{});
+    auto gate = [&](uint32_t q, bool block) {
+      const uint32_t seq = seq0 + q;
+      // sender: the slot was consumed (ack in MY pad); receiver: the chunk landed (ready in MY pad)
+      const uint32_t *flag = SEND ? ack : ready + seq % kP2PSlots;
+      const uint32_t target = SEND ? seq + 1u - kP2PSlots : seq + 1u;
+      if (block) {
+        if (!wait_flag_ge(c, flag, target)) return -1;
+      } else if (int32_t(ld_acquire_sys(flag) - target) < 0) {
+        return 0;
+      }
+      if (!SEND) fence_proxy_async();  // the peer's stores before our bulk reads
+      return 1;
+    };
+    auto done = [&](uint32_t q) {
+      __threadfence_block();
+      mailbox = q + 1;
+    };
+    // the sender's stores cross NVLink, the receiver's stay in local HBM
+    const bool ok = SEND ? bulk_copy_segments<BulkRemote>(br, nq32, seg, gate, done)
+                         : bulk_copy_segments<BulkLocal>(br, nq32, seg, gate, done);
     if (!ok) stop = 1;
   } else if (threadIdx.x == 32 && nq > 0) {
     // ---- flag thread: publishes "ready" (sender) / "ack" (receiver) for completed chunks ------
@@ -267,7 +235,7 @@ static int p2p_common(b200_comm *c, void *buf, size_t nbytes, int peer, cudaStre
   const size_t nchunks = (nbytes + chunk - 1) / chunk;
   // Grid is a pure function of the message size so both sides pair CTA b with CTA b.
   int g = int(nchunks < size_t(kP2PRings) ? nchunks : size_t(kP2PRings));
-  P2PArgs a{static_cast<char *>(buf), nbytes, chunk, peer, int(c->params[B200_PARAM_BULK_CFG])};
+  P2PArgs a{static_cast<char *>(buf), nbytes, chunk, peer};
   // The protocol (rings, slots, chunking) is a function of the message size alone; HOW this side
   // moves its bytes is a local choice: the bulk-copy unit when the tensor is 16-byte aligned, a
   // whole number of 16-byte units and the chunks are big enough to be worth a TMA pipeline.

@@ -28,7 +28,7 @@ template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.
 
 // mode 0: copy (load+store), 1: loads only, 2: stores only.  LANES issuing threads per CTA (warp w,
 // lane 0), each with its own ring of STAGES tiles.
-template <int STAGES, int LA, int LANES>
+template <int STAGES, int LA, int LANES, int LAG = -1>
 __global__ void __launch_bounds__(512, 1) bench_kernel(const char *src, char *dst, size_t bytes_per_lane, uint32_t tile, int mode) {
   extern __shared__ __align__(128) char smem[];
   const int lane_id = threadIdx.x / 32;
@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(512, 1) bench_kernel(const char *src, char *ds
       bulk_s2g(dst + base + size_t(sj) * tile, ring + s * tile, tile);
       bulk_commit();
       bulk_wait_read<RP>();
+      if (LAG >= 0 && sj >= LAG) bulk_wait<(LAG >= 0 ? LAG : 0)>();
     }
     ++sj;
   }
@@ -75,11 +76,11 @@ __global__ void ldst_kernel(const uint4 *src, uint4 *dst, size_t units) {
   }
 }
 
-template <int STAGES, int LA, int LANES>
+template <int STAGES, int LA, int LANES, int LAG = -1>
 static void run(const char *name, const char *src, char *dst, int ctas, uint32_t tile, int mode, size_t total) {
   const size_t smem = size_t(LANES) * STAGES * tile + LANES * STAGES * 8 + 128;
   if (smem > 227 * 1024) return;
-  auto k = bench_kernel<STAGES, LA, LANES>;
+  auto k = bench_kernel<STAGES, LA, LANES, LAG>;
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   size_t per_lane = total / (size_t(ctas) * LANES) / tile * tile;
   cudaEvent_t a, b;
@@ -94,8 +95,8 @@ static void run(const char *name, const char *src, char *dst, int ctas, uint32_t
     if (rep && ms < best) best = ms;
   }
   const double gb = double(per_lane) * ctas * LANES / 1e9;
-  printf("%-8s mode=%d ctas=%3d lanes=%d tile=%3uK stages=%2d la=%d : %8.1f us  %7.1f GB/s  (%.1f GB/s per CTA)\n", name, mode, ctas, LANES,
-         tile >> 10, STAGES, LA, best * 1e3, gb / (best * 1e-3), gb / (best * 1e-3) / ctas);
+  printf("%-8s mode=%d ctas=%3d lanes=%d tile=%3uK stages=%2d la=%d lag=%2d : %8.1f us  %7.1f GB/s  (%.1f GB/s per CTA)\n", name, mode, ctas, LANES,
+         tile >> 10, STAGES, LA, LAG, best * 1e3, gb / (best * 1e-3), gb / (best * 1e-3) / ctas);
   fflush(stdout);
 }
 
@@ -114,51 +115,23 @@ int main() {
       CK(cudaDeviceEnablePeerAccess(1, 0));
     }
   }
-  if (rdst) {
-    // pull direction: source on the PEER, destination local
-    for (int ctas : {1, 8, 16, 32}) {
-      run<6, 3, 1>("rload", rdst, dst, ctas, 32 << 10, 1, total);   // TMA loads only, from the peer
-      run<6, 5, 1>("rload", rdst, dst, ctas, 32 << 10, 1, total);
-      run<12, 11, 1>("rload", rdst, dst, ctas, 16 << 10, 1, total);
-      run<6, 3, 1>("rpull", rdst, dst, ctas, 32 << 10, 0, total);   // peer -> smem -> local HBM
-      run<6, 5, 1>("rpull", rdst, dst, ctas, 32 << 10, 0, total);
-    }
-    for (int ctas : {8, 16, 32, 64, 148}) {
-      cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-      float best = 1e9;
-      for (int rep = 0; rep < 4; ++rep) {
-        CK(cudaEventRecord(a));
-        ldst_kernel<<<ctas, 512>>>((const uint4 *)rdst, (uint4 *)dst, total / 16);
-        CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
-        float ms; CK(cudaEventElapsedTime(&ms, a, b));
-        if (rep && ms < best) best = ms;
-      }
-      printf("rpull    ld/st 512thr x8  ctas=%3d : %8.1f us  %7.1f GB/s (%.1f per CTA)\n", ctas, best * 1e3, total / 1e9 / (best * 1e-3), total / 1e9 / (best * 1e-3) / ctas);
-    }
-  }
   for (int remote = 0; remote < (rdst ? 2 : 1); ++remote) {
     char *d = remote ? rdst : dst;
     const char *nm = remote ? "remote" : "local";
-    for (int ctas : {1, 8, 16, 32}) {
-      for (int mode : {0, 1, 2}) {
-        if (remote && mode == 1) continue;
-        run<6, 3, 1>(nm, src, d, ctas, 32 << 10, mode, total);
-      }
-      run<6, 5, 1>(nm, src, d, ctas, 32 << 10, 0, total);
+    for (int ctas : {1, 16}) {
+      run<6, 3, 1>(nm, src, d, ctas, 32 << 10, 0, total);
+      run<6, 3, 1, 2>(nm, src, d, ctas, 32 << 10, 0, total);
+      run<6, 3, 1, 3>(nm, src, d, ctas, 32 << 10, 0, total);
+      run<6, 3, 1, 4>(nm, src, d, ctas, 32 << 10, 0, total);
+      run<6, 3, 1, 6>(nm, src, d, ctas, 32 << 10, 0, total);
+      run<6, 3, 1, 8>(nm, src, d, ctas, 32 << 10, 0, total);
+      run<6, 3, 1, 12>(nm, src, d, ctas, 32 << 10, 0, total);
+      run<6, 3, 1, 16>(nm, src, d, ctas, 32 << 10, 0, total);
+      run<6, 3, 1, 24>(nm, src, d, ctas, 32 << 10, 0, total);
       run<6, 4, 1>(nm, src, d, ctas, 32 << 10, 0, total);
-      run<3, 2, 2>(nm, src, d, ctas, 32 << 10, 0, total);
-    }
-    for (int ctas : {8, 16, 32, 64, 148}) {
-      cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-      float best = 1e9;
-      for (int rep = 0; rep < 4; ++rep) {
-        CK(cudaEventRecord(a));
-        ldst_kernel<<<ctas, 512>>>((const uint4 *)src, (uint4 *)d, total / 16);
-        CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
-        float ms; CK(cudaEventElapsedTime(&ms, a, b));
-        if (rep && ms < best) best = ms;
-      }
-      printf("%-8s ld/st 512thr x8  ctas=%3d : %8.1f us  %7.1f GB/s (%.1f per CTA)\n", nm, ctas, best * 1e3, total / 1e9 / (best * 1e-3), total / 1e9 / (best * 1e-3) / ctas);
+      run<6, 4, 1, 12>(nm, src, d, ctas, 32 << 10, 0, total);
+      run<12, 6, 1, 12>(nm, src, d, ctas, 16 << 10, 0, total);
+      run<12, 6, 1, 24>(nm, src, d, ctas, 16 << 10, 0, total);
     }
   }
   return 0;

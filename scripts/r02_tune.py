@@ -54,7 +54,7 @@ def allreduce(g, args):
             for vname, v in variants:
                 set_all(g, N.PARAM_PIPE_VARIANT, v)
                 if vname == "pull":
-                    grid = [(1, 8, 24), (1, 16, 16), (1, 16, 24), (1, 16, 32), (1, 16, 48), (1, 32, 24), (1, 32, 32), (2, 16, 24)]
+                    grid = [(1, 16, 16), (1, 16, 24), (1, 16, 32), (1, 16, 48), (1, 16, 64), (1, 32, 32), (1, 32, 48), (2, 16, 32)]
                 elif vname == "push":
                     grid = [(1, 16, 32), (1, 16, 48), (1, 16, 64), (1, 32, 48), (1, 32, 64), (1, 32, 96), (2, 16, 48), (2, 32, 64)]
                 else:
@@ -80,9 +80,7 @@ def sendrecv(g, args):
         xs = [torch.ones(size // 4, device=g.device(r)) for r in range(n)]
         iters = 20 if size <= 64 * MiB else 6
         call = lambda c, r: (c.send(xs[0], 1) if r == 0 else (c.recv(xs[1], 0) if r == 1 else None))  # noqa: E731
-        for label, v, cfg in (("ld/st", 0, -1), ("bulk", -1, -1), ("bulk la3 lag10", -1, 1), ("bulk la3 lag16", -1, 2),
-                              ("bulk la5 lag16", -1, 3), ("bulk la5 lag24", -1, 4), ("bulk la4 lag16", -1, 5),
-                              ("bulk la3 lag24", -1, 6)):
+        for label, v, cfg in (("ld/st", 0, -1), ("bulk", -1, -1)):
             set_all(g, N.PARAM_P2P_BULK_MIN_CHUNK, v)
             set_all(g, N.PARAM_BULK_CFG, cfg)
             us = time_graphs(g, call, iters)

@@ -43,7 +43,7 @@ by_cta = defaultdict(list)
 for ns, cta, e, a in ev:
     by_cta[cta].append(((ns - t0) / 1e3, e, a))
 names = {1: "load", 2: "store", 3: "ringok", 4: "done<", 5: "drain", 6: "gateok", 9: "flag:see", 10: "flag:proxyfenced", 13: "flag:sysfenced", 11: "flag:arrived", 12: "flag:signal",
-         20: "red:wait", 21: "red:go", 22: "red:itemend", 23: "red:arrived", 41: "o:load", 42: "o:store", 43: "o:ringok", 44: "o:done<",
+         30: "pl:load", 31: "pl:gatewait", 32: "pl:gateok", 33: "pl:landed", 20: "red:wait", 21: "red:go", 22: "red:itemend", 23: "red:arrived", 41: "o:load", 42: "o:store", 43: "o:ringok", 44: "o:done<",
          45: "o:drain", 46: "o:gateok"}
 for cta in [int(x) for x in args.ctas.split(",")]:
     rows = by_cta.get(cta, [])

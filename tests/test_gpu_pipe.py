@@ -38,10 +38,8 @@ def _variants(g, world):
     from ray_b200 import _native as N
 
     out = [("peer", 2)]
-    if (world - 1) * max(SIZES) <= (40 << 20):
-        out.append(("push", 0))
     if world == 2:
-        out.append(("pull", 3))
+        out += [("pull", 3), ("push", 0)]
     if g.has_multicast:
         out.append(("nvls", 1))
     return out, N
@@ -88,8 +86,14 @@ def test_pipelined_allreduce_matches_oracle(pipe_groups, world):
                                                    accumulate="fp32" if half else "native")
                     for r in range(world):
                         got = _np(xs[r])
-                        assert np.array_equal(got.view(np.uint8), np.asarray(want).view(np.uint8)), \
-                            (vname, world, dtype, op, nbytes, r)
+                        if vname == "nvls":
+                            # the switch may return +0.0 where IEEE gives -0.0 (observed): compare values
+                            assert np.array_equal(got.astype(np.float64), np.asarray(want).astype(np.float64)), \
+                                (vname, world, dtype, op, nbytes, r)
+                            assert np.array_equal(got.view(np.uint8), _np(xs[0]).view(np.uint8))  # replicas agree
+                        else:
+                            assert np.array_equal(got.view(np.uint8), np.asarray(want).view(np.uint8)), \
+                                (vname, world, dtype, op, nbytes, r)
         finally:
             for c in g.comms:
                 c.set_param(N.PARAM_PIPE_VARIANT, -1)
