@@ -144,6 +144,39 @@ __device__ __forceinline__ int thread_wait_chunk(const DevComm &c, size_t flag_b
   return 1;
 }
 
+// Scout thread: the consumers of a chunk flag (copy-out, pull) must not pay for the flag wait in
+// their issue loop -- an ld.acquire.sys poll of n flags plus fence.proxy.async measured ~2 us per
+// chunk (profiles/r02/trace_pull_v1.log), more than the chunk's copy time.  A spare thread walks
+// the chunks in order, does the acquiring waits and the proxy fence, and publishes its progress in
+// shared memory; the consumer's gate is then one shared-memory load.
+struct ChunkScout {
+  volatile uint32_t ready;  // chunks [0, ready) are flagged by every rank
+  volatile int stop;
+};
+__device__ __forceinline__ void scout_thread(const DevComm &c, size_t flag_base, uint32_t value, uint32_t nchunks,
+                                             ChunkScout *sc) {
+  for (uint32_t k = 0; k < nchunks; ++k) {
+    const uint32_t *f = c.sig[c.rank] + flag_base + size_t(k) * kMaxRanks;
+    for (int p = 0; p < c.world; ++p) {
+      if (!wait_flag_ge(c, f + p, value)) {
+        sc->stop = 1;
+        return;
+      }
+    }
+    fence_proxy_async();  // the flagged stores (generic proxy) before the consumer's bulk reads
+    __threadfence_block();
+    sc->ready = k + 1;
+  }
+}
+__device__ __forceinline__ int scout_gate(ChunkScout *sc, uint32_t k, bool block) {
+  if (sc->ready > k) return 1;
+  if (!block) return 0;
+  while (sc->ready <= k) {
+    if (sc->stop) return -1;
+  }
+  return 1;
+}
+
 // Flag thread of a copy-in / push CTA: publish flag0 of every chunk this CTA finished.
 __device__ __forceinline__ void copy_flag_thread(const DevComm &c, const PipeGeom &g, CopyMailbox *mb,
                                                  uint32_t nchunks, uint32_t value) {
@@ -293,22 +326,25 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
     }
   } else {
     // ---- copy-out ------------------------------------------------------------------------
-    const BulkRing ring = bulk_ring_init(dyn_smem);
+    __shared__ ChunkScout sc;
     if (threadIdx.x == 0) {
-      const uint32_t j = uint32_t(b - G - Gr);
+      sc.ready = 0;
+      sc.stop = 0;
+    }
+    const BulkRing ring = bulk_ring_init(dyn_smem);
+    const uint32_t j = uint32_t(b - G - Gr);
+    const uint32_t my_chunks = chunks_of_cta(g, j);
+    if (threadIdx.x == 0) {
       const char *slot = c.data[r] + off;
       bulk_copy_segments<BulkLocal>(
-          ring, chunks_of_cta(g, j),
+          ring, my_chunks,
           [&](uint32_t k) {
             const size_t o = share_off(g, j, k);
             return BulkSeg{slot + o, a.out + o, share_len(g, j, k)};
           },
-          [&](uint32_t k, bool block) {
-            const int st = thread_wait_chunk(c, kSigPipe1, k, ep + 2, block);
-            if (st == 1) fence_proxy_async();  // peers' stores (generic proxy) before our bulk reads (async proxy)
-            return st;
-          },
-          [&](uint32_t) {});
+          [&](uint32_t k, bool block) { return scout_gate(&sc, k, block); }, [&](uint32_t) {});
+    } else if (threadIdx.x == 32) {
+      scout_thread(c, kSigPipe1, ep + 2, my_chunks, &sc);
     }
   }
   finish_launch(c);
@@ -448,7 +484,7 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
 }
 
 template <typename T, int OP>
-__global__ void __launch_bounds__(kThreads, 1) allreduce_pull_kernel(DevComm c, PipeArgs a) {
+__global__ void __launch_bounds__(kThreads + 32, 1) allreduce_pull_kernel(DevComm c, PipeArgs a) {
   extern __shared__ __align__(128) char dyn_smem[];
   using Tr = Traits<T>;
   const uint32_t launch = c.st->launch_ctr;
@@ -463,11 +499,14 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pull_kernel(DevComm c, 
     role_copy_in(c, a, g, off, ep, dyn_smem, uint32_t(b));
   } else {
     __shared__ int bail;
+    __shared__ ChunkScout sc;
     const uint32_t tiles_smem = smem_u32(dyn_smem);
     const uint32_t full = tiles_smem + kBulkStages * kBulkTile;  // mbarriers: tile landed
     const uint32_t empty = full + 8 * kBulkStages;               // mbarriers: tile consumed
     if (threadIdx.x == 0) {
       bail = 0;
+      sc.ready = 0;
+      sc.stop = 0;
       for (int s = 0; s < kBulkStages; ++s) {
         mbar_init(full + 8 * s, 1);
         mbar_init(empty + 8 * s, kThreads);
@@ -483,24 +522,23 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pull_kernel(DevComm c, 
     const uint32_t nt = total_tiles > me ? (total_tiles - 1 - me) / uint32_t(Gr) + 1 : 0;  // tiles me, me+Gr, ...
     const uint32_t tiles_per_chunk = uint32_t(g.C / kPullTile);
     const char *peer_slot = c.data[peer] + off;
-    uint32_t next_load = 0, ready_chunks = 0;
+    if (threadIdx.x >= kThreads) {
+      // service warp (the kernel runs kThreads + 32 threads): its first lane is the scout.  A chunk
+      // is usable once BOTH ranks flagged it: the peer's slot is readable, and the local copy-in
+      // CTAs are done reading the caller's tensor, so it may be overwritten in place.
+      if (threadIdx.x == kThreads && nt > 0) scout_thread(c, kSigPipe0, ep + 1, g.K, &sc);
+      finish_launch(c);
+      return;
+    }
+    uint32_t next_load = 0;
     for (uint32_t it = 0; it < nt; ++it) {
       if (threadIdx.x == 0) {
         // keep the ring full: tiles it .. it + kPullLookahead
         while (next_load < nt && next_load <= it + uint32_t(kPullLookahead)) {
           const uint32_t t = me + next_load * uint32_t(Gr);
-          const uint32_t k = t / tiles_per_chunk;
-          if (k >= ready_chunks) {
-            // chunk k staged by the peer (its slot is readable) AND by the local copy-in CTAs (the
-            // caller's tensor may be overwritten in place)
-            if (next_load == it) trace_event(c, 31, k);
-            const int st = thread_wait_chunk(c, kSigPipe0, k, ep + 1, next_load == it);
-            if (st < 0) bail = 1;
-            if (st <= 0) break;
-            ready_chunks = k + 1;
-            fence_proxy_async();
-            trace_event(c, 32, k);
-          }
+          const int st = scout_gate(&sc, t / tiles_per_chunk, next_load == it);
+          if (st < 0) bail = 1;
+          if (st <= 0) break;
           const uint32_t s = next_load % kBulkStages;
           if (next_load >= uint32_t(kBulkStages)) {  // stage consumed by everyone?
             const uint32_t par = (next_load / kBulkStages - 1) & 1u;
@@ -624,7 +662,7 @@ int launch_allreduce_pipe(b200_comm *c, const char *in, char *out, size_t nbytes
     }
     auto k = allreduce_pull_kernel<T, OP>;
     if ((rc = set_dyn_smem(c->device, reinterpret_cast<const void *>(k)))) return rc;
-    k<<<grid, kThreads, kBulkSmemBytes, stream>>>(dc, a);
+    k<<<grid, kThreads + 32, kBulkSmemBytes, stream>>>(dc, a);  // + one service warp (scout)
   } else if (variant == PIPE_PUSH) {
     if (c->world != 2) {
       set_error("the push all-reduce is a 2-rank kernel");

@@ -56,11 +56,11 @@ def allreduce(g, args):
                 if vname == "pull":
                     grid = [(1, 16, 16), (1, 16, 24), (1, 16, 32), (1, 16, 48), (1, 16, 64), (1, 32, 32), (1, 32, 48), (2, 16, 32)]
                 elif vname == "push":
-                    grid = [(1, 16, 32), (1, 16, 48), (1, 16, 64), (1, 32, 48), (1, 32, 64), (1, 32, 96), (2, 16, 48), (2, 32, 64)]
+                    grid = [(1, 16, 48), (1, 16, 64), (1, 16, 96), (1, 16, 128), (1, 8, 64), (2, 16, 64), (2, 16, 96), (4, 16, 96)]
                 else:
                     grid = [(1, 8, 48), (1, 16, 32), (1, 16, 48), (1, 16, 64), (1, 16, 96), (1, 32, 64), (2, 16, 48), (2, 16, 64),
                             (4, 16, 64)]
-                if args.quick:
+                if args.quick and vname != 'push':
                     grid = grid[1:4]
                 for chunk_mib, copy, red in grid:
                     set_all(g, N.PARAM_PIPE_CHUNK_BYTES, chunk_mib * MiB)
