@@ -233,11 +233,55 @@ __device__ __forceinline__ void role_copy_in(const DevComm &c, const PipeArgs &a
 constexpr int kItemUnroll = 4;
 constexpr size_t kItemUnits = size_t(kThreads) * kItemUnroll;  // 16-byte units per reduce work item
 
+// The reduce work of one rank: chunk k's stripe [lo, hi) (16-byte units) is cut into items of
+// kItemUnits units; items are dealt round-robin, chunk-major, to the Gr reduce CTAs.  Workers and
+// the arrival thread of a CTA walk the same sequence.
+struct ItemIter {
+  const PipeGeom &g;
+  uint32_t rank, world, me, Gr;
+  uint32_t k = 0;        // next chunk to look at
+  size_t item_base = 0;  // global index of chunk k's first item
+  // the item most recently returned by next():
+  size_t lo = 0, hi = 0, it = 0;
+  uint32_t nitems = 0, cur_k = 0;
+  bool in_chunk = false;
+  __device__ ItemIter(const PipeGeom &g_, int r, int n, uint32_t me_, uint32_t Gr_)
+      : g(g_), rank(uint32_t(r)), world(uint32_t(n)), me(me_), Gr(Gr_) {}
+  __device__ bool next(uint32_t &k_out) {
+    if (in_chunk) {
+      it += Gr;
+      if (it < nitems) {
+        k_out = cur_k;
+        return true;
+      }
+      in_chunk = false;
+    }
+    for (; k < g.K; ++k) {
+      const size_t cu = chunk_len(g, k) >> 4;
+      lo = cu * size_t(rank) / size_t(world);
+      hi = cu * size_t(rank + 1) / size_t(world);
+      const size_t items = (hi - lo + kItemUnits - 1) / kItemUnits;
+      nitems = uint32_t(items ? items : 1);  // an empty stripe still publishes
+      it = (size_t(me) + size_t(Gr) - item_base % size_t(Gr)) % size_t(Gr);
+      item_base += nitems;
+      if (it < nitems) {
+        cur_k = k_out = k;
+        ++k;
+        in_chunk = true;
+        return true;
+      }
+    }
+    return false;
+  }
+  // the scout only has to follow the chunks up to the last one this CTA works on
+  __device__ uint32_t last_chunk_needed() const { return g.K; }
+};
+
 // ---------------------------------------------------------------------------
 // n >= 3: copy-in | reduce (NVLS or peer ld/st) | copy-out
 // ---------------------------------------------------------------------------
 template <typename T, int OP, bool NVLS>
-__global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, PipeArgs a) {
+__global__ void __launch_bounds__(kThreads + 32, 1) allreduce_pipe_kernel(DevComm c, PipeArgs a) {
   extern __shared__ __align__(128) char dyn_smem[];
   using Tr = Traits<T>;
   const uint32_t launch = c.st->launch_ctr;
@@ -252,23 +296,59 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
     role_copy_in(c, a, g, off, ep, dyn_smem, uint32_t(b));
   } else if (b < G + Gr) {
     // ---- reduce ------------------------------------------------------------------------------
-    const int me = b - G;
-    size_t item_base = 0;  // global index of chunk k's first work item
-    for (uint32_t k = 0; k < g.K; ++k) {
-      const size_t cu = chunk_len(g, k) >> 4;           // units in this chunk
-      const size_t lo = cu * size_t(r) / size_t(n);     // this rank's stripe
-      const size_t hi = cu * size_t(r + 1) / size_t(n);
-      const size_t items = (hi - lo + kItemUnits - 1) / kItemUnits;
-      const size_t nitems = items ? items : 1;          // an empty stripe still publishes
-      size_t it = (size_t(me) + size_t(Gr) - item_base % size_t(Gr)) % size_t(Gr);
-      item_base += nitems;
-      if (it >= nitems) continue;
-      if (threadIdx.x == 0) trace_event(c, 20, k);
-      if (!cta_wait_chunk(c, kSigPipe0, k, ep + 1)) break;
-      if (threadIdx.x == 0) trace_event(c, 21, k);
-      const size_t cbase = off + size_t(k) * g.C;
-      for (; it < nitems; it += size_t(Gr)) {
-        const size_t u0 = lo + it * kItemUnits + threadIdx.x;
+    // 512 workers + one service warp (the kernel runs kThreads + 32 threads).  The workers only
+    // load, reduce and store; waiting for chunk flags (scout, service lane 0) and publishing
+    // arrivals behind a system-scope fence (service lane 1) happen beside them, so a worker never
+    // executes a fence or an acquiring poll.
+    __shared__ ChunkScout sc;
+    __shared__ CopyMailbox mb;  // chunks_done counts this CTA's finished work items here
+    if (threadIdx.x == 0) {
+      sc.ready = 0;
+      sc.stop = 0;
+      mb.chunks_done = 0;
+      mb.stop = 0;
+    }
+    __syncthreads();
+    ItemIter iter(g, r, n, uint32_t(b - G), uint32_t(Gr));
+    if (threadIdx.x >= kThreads) {
+      if (threadIdx.x == kThreads) {
+        scout_thread(c, kSigPipe0, ep + 1, iter.last_chunk_needed(), &sc);
+      } else if (threadIdx.x == kThreads + 1) {
+        uint32_t published = 0, k = 0;
+        bool have = iter.next(k);
+        while (have) {
+          const uint32_t avail = mb.chunks_done;
+          if (avail == published) {
+            if (mb.stop) break;
+            __nanosleep(100);
+            continue;
+          }
+          __threadfence_block();
+          __threadfence_system();  // one fence for every item finished so far
+          for (; published < avail && have; ++published) {
+            if (chunk_arrive_fenced(&c.st->pipe_cnt[1][k], iter.nitems))
+              signal_all(c, kSigPipe1 + size_t(k) * kMaxRanks, ep + 2);
+            have = iter.next(k);
+          }
+        }
+      }
+    } else {
+      uint32_t k = 0, done_items = 0;
+      while (iter.next(k)) {
+        // chunk k staged on every rank?
+        if (sc.ready <= k) {
+          bool alive = true;
+          while (sc.ready <= k) {
+            if (sc.stop) {
+              alive = false;
+              break;
+            }
+          }
+          if (!alive) break;
+        }
+        const size_t cbase = off + size_t(k) * g.C;
+        const size_t hi = iter.hi;
+        const size_t u0 = iter.lo + iter.it * kItemUnits + threadIdx.x;
         if (NVLS) {
           char *mc = c.mc_data + cbase;
           uint4 v[kItemUnroll];
@@ -290,39 +370,44 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_pipe_kernel(DevComm c, 
             }
           }
         } else {
-#pragma unroll 2
-          for (int q = 0; q < kItemUnroll; ++q) {
-            const size_t u = u0 + size_t(q) * kThreads;
-            if (u < hi) {
-              uint4 v[kMaxRanks];
+#pragma unroll 1
+          for (int q0 = 0; q0 < kItemUnroll; q0 += 2) {
+            uint4 v[2][kMaxRanks];
 #pragma unroll
-              for (int p = 0; p < kMaxRanks; ++p)
-                if (p < n) v[p] = ld_peer(c.data[p] + cbase + (u << 4));
-              typename Tr::Acc acc = Tr::unpack(v[0]);
+            for (int q = 0; q < 2; ++q) {
+              const size_t u = u0 + size_t(q0 + q) * kThreads;
+              if (u < hi) {
 #pragma unroll
-              for (int p = 1; p < kMaxRanks; ++p)
-                if (p < n) Tr::template reduce<OP>(acc, Tr::unpack(v[p]));  // rank-ascending
-              if (OP == B200_AVG) Tr::average(acc, n);
-              const uint4 res = Tr::pack(acc);
+                for (int p = 0; p < kMaxRanks; ++p)
+                  if (p < n) v[q][p] = ld_peer(c.data[p] + cbase + (u << 4));
+              }
+            }
 #pragma unroll
-              for (int i = 0; i < kMaxRanks; ++i) {
-                if (i < n) {
-                  int p = r + i;
-                  if (p >= n) p -= n;
-                  st_vec(c.data[p] + cbase + (u << 4), res);
+            for (int q = 0; q < 2; ++q) {
+              const size_t u = u0 + size_t(q0 + q) * kThreads;
+              if (u < hi) {
+                typename Tr::Acc acc = Tr::unpack(v[q][0]);
+#pragma unroll
+                for (int p = 1; p < kMaxRanks; ++p)
+                  if (p < n) Tr::template reduce<OP>(acc, Tr::unpack(v[q][p]));  // rank-ascending
+                if (OP == B200_AVG) Tr::average(acc, n);
+                const uint4 res = Tr::pack(acc);
+#pragma unroll
+                for (int i = 0; i < kMaxRanks; ++i) {
+                  if (i < n) {
+                    int p = r + i;
+                    if (p >= n) p -= n;
+                    st_vec(c.data[p] + cbase + (u << 4), res);
+                  }
                 }
               }
             }
           }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          trace_event(c, 22, k);
-          if (chunk_arrive(&c.st->pipe_cnt[1][k], uint32_t(nitems)))
-            signal_all(c, kSigPipe1 + size_t(k) * kMaxRanks, ep + 2);
-          trace_event(c, 23, k);
-        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");  // workers only
+        if (threadIdx.x == 0) mailbox_post(&mb, ++done_items);
       }
+      if (threadIdx.x == 0 && sc.stop) mb.stop = 1;
     }
   } else {
     // ---- copy-out ------------------------------------------------------------------------
@@ -675,7 +760,7 @@ int launch_allreduce_pipe(b200_comm *c, const char *in, char *out, size_t nbytes
     if constexpr (Multimem<T>::kSum && (OP == B200_SUM || OP == B200_AVG)) {
       auto k = allreduce_pipe_kernel<T, OP, true>;
       if ((rc = set_dyn_smem(c->device, reinterpret_cast<const void *>(k)))) return rc;
-      k<<<grid, kThreads, kBulkSmemBytes, stream>>>(dc, a);
+      k<<<grid, kThreads + 32, kBulkSmemBytes, stream>>>(dc, a);  // + one service warp
     } else {
       set_error("NVLS all-reduce supports SUM/AVG on f32/f16/bf16 only");
       return B200_ERR_UNSUPPORTED;
@@ -683,7 +768,7 @@ int launch_allreduce_pipe(b200_comm *c, const char *in, char *out, size_t nbytes
   } else {
     auto k = allreduce_pipe_kernel<T, OP, false>;
     if ((rc = set_dyn_smem(c->device, reinterpret_cast<const void *>(k)))) return rc;
-    k<<<grid, kThreads, kBulkSmemBytes, stream>>>(dc, a);
+    k<<<grid, kThreads + 32, kBulkSmemBytes, stream>>>(dc, a);  // + one service warp
   }
   B200_LAUNCH_CHECK(c);
   return B200_OK;

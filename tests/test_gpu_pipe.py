@@ -118,7 +118,13 @@ def test_pipelined_allreduce_out_of_place_and_back_to_back(pipe_groups, world):
             o.zero_()
         g.run(lambda c, r: c.allreduce(ins[r], N.SUM, out=outs[r], algo=N.ALGO_PIPE))
         for r in range(world):
-            assert np.array_equal(outs[r].cpu().numpy(), want), (world, rep)
+            got = outs[r].cpu().numpy()
+            if g.has_multicast and world > 2:  # NVLS roles: the switch picks the summation order
+                bound = 1e-6 * np.sum([np.abs(h.numpy().astype(np.float64)) for h in host], axis=0)
+                assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= bound), (world, rep)
+                assert np.array_equal(got, outs[0].cpu().numpy())  # replicas bit-identical
+            else:
+                assert np.array_equal(got, want), (world, rep)
             assert torch.equal(ins[r].cpu(), host[r])  # inputs untouched
         if rep % 2:
             ys = [s.clone() for s in small]
