@@ -295,7 +295,9 @@ static size_t ll_limit(const b200_comm *c) {
 static size_t pipe_min_bytes(const b200_comm *c) {
   const long long v = c->params[B200_PARAM_PIPE_MIN_BYTES];
   if (v >= 0) return size_t(v);
-  return size_t(8) << 20;
+  // 2 ranks: the pull kernel wins from 16 MiB (350 vs 330 GB/s; 64 MiB 519 vs 440, 1 GiB 619 vs 411);
+  // NVLS roles: from 128 MiB (8 ranks: 586 vs 559, 256 MiB 673 vs 611, 1 GiB 694 vs 627 GB/s)
+  return c->world == 2 ? (size_t(16) << 20) : (size_t(128) << 20);
 }
 
 static size_t oneshot_limit(const b200_comm *c) {
@@ -355,7 +357,7 @@ extern "C" int b200_allreduce(b200_comm_t c, const void *in, void *out, size_t c
   // the two staging passes with the NVLink phase (allreduce_pipe.cu).  They move whole 16-byte
   // units with the bulk-copy engine, so they need aligned operands.
   int pipe_variant = -1;
-  if (sym_off < 0 && is_aligned16(in) && is_aligned16(out) && (total & 15) == 0 &&
+  if (sym_off < 0 && is_aligned16(in) && is_aligned16(out) && (total & 15) == 0 && pipe_max_bytes(c, 0) > 0 &&
       (algo == B200_ALGO_PIPE || (algo == B200_ALGO_AUTO && total >= pipe_min_bytes(c)))) {
     if (c->world == 2) pipe_variant = PIPE_PULL;
     else if (c->mc_active && nvls_capable(dtype, op)) pipe_variant = PIPE_NVLS;

@@ -702,19 +702,28 @@ int set_dyn_smem(int device, const void *fn) {
   return B200_OK;
 }
 
+// Defaults measured on 2 / 4 / 8 B200s (profiles/r02/tune_n2.log, tune_n4.log, tune_n8.log):
+//   2 ranks (pull)      : 1 MiB chunks, 32 copy-in + 32 pull CTAs
+//   3-4 ranks (NVLS)    : 4 MiB chunks, 16 + 16 copy CTAs, 64 reduce CTAs
+//   5-8 ranks (NVLS)    : 8 MiB chunks, 16 + 16 copy CTAs, 32 reduce CTAs (more CTAs on the
+//                         switch reduction measured slower, as in round 1)
+size_t pipe_chunk_bytes(const b200_comm *c) {
+  const long long v = c->params[B200_PARAM_PIPE_CHUNK_BYTES];
+  size_t C = v > 0 ? size_t(v) : (c->world == 2 ? (size_t(1) << 20) : (c->world <= 4 ? (size_t(4) << 20) : (size_t(8) << 20)));
+  const size_t quantum = size_t(32) * kBulkTile;  // C / G is a whole number of tiles for any power-of-two G <= 32
+  C = round_up(C, quantum);
+  const size_t fit = c->staging_bytes / quantum * quantum;  // a chunk must fit the staging slot
+  return C < fit ? C : fit;                                 // 0: slot too small for the pipeline
+}
+
 size_t pipe_max_bytes(const b200_comm *c, int variant) {
+  (void)variant;
   const size_t C = pipe_chunk_bytes(c);
+  if (C == 0) return 0;
   size_t cap = c->staging_bytes;
   const size_t by_chunks = size_t(kMaxPipeChunks) * C;
   cap = cap < by_chunks ? cap : by_chunks;
   return cap / C * C;  // whole chunks, so a split message continues on a chunk boundary
-}
-
-size_t pipe_chunk_bytes(const b200_comm *c) {
-  const long long v = c->params[B200_PARAM_PIPE_CHUNK_BYTES];
-  size_t C = v > 0 ? size_t(v) : (size_t(1) << 20);
-  const size_t quantum = size_t(32) * kBulkTile;  // C / G is a whole number of tiles for any power-of-two G <= 32
-  return round_up(C, quantum);
 }
 
 template <typename T, int OP>
@@ -723,8 +732,8 @@ int launch_allreduce_pipe(b200_comm *c, const char *in, char *out, size_t nbytes
   PipeArgs a{in, out, nbytes, c->staging_bytes, pipe_chunk_bytes(c), 0};
   const long long pc = c->params[B200_PARAM_PIPE_COPY_CTAS];
   const long long pr = c->params[B200_PARAM_PIPE_RED_CTAS];
-  int G = pc > 0 ? int(pc) : (variant == PIPE_NVLS || variant == PIPE_PEER ? 8 : 16);
-  int Gr = pr > 0 ? int(pr) : (variant == PIPE_PULL ? 32 : 48);
+  int G = pc > 0 ? int(pc) : (variant == PIPE_PULL ? 32 : 16);
+  int Gr = pr > 0 ? int(pr) : (variant == PIPE_PULL ? 32 : (variant == PIPE_PUSH ? 64 : (c->world <= 4 ? 64 : 32)));
   const int roles = (variant == PIPE_PUSH || variant == PIPE_PULL) ? 1 : 2;
   int cap = c->forced_blocks > 0 ? c->forced_blocks : c->sm_count;
   if (roles * G + Gr > cap) {  // shared-GPU harness / small parts: shrink, keep at least one reducer

@@ -31,7 +31,7 @@ def set_all(g, param, value):
 def allreduce(g, args):
     n = g.world_size
     factor = 2 * (n - 1) / n
-    sizes = [16 * MiB, 64 * MiB, 256 * MiB] if args.quick else [8 * MiB, 16 * MiB, 32 * MiB, 64 * MiB, 256 * MiB, 1024 * MiB]
+    sizes = [16 * MiB, 64 * MiB, 256 * MiB] if args.quick else [16 * MiB, 32 * MiB, 64 * MiB, 128 * MiB, 256 * MiB, 1024 * MiB]
     for dtype in (torch.float32,):
         for size in sizes:
             numel = size // 4
@@ -58,8 +58,7 @@ def allreduce(g, args):
                 elif vname == "push":
                     grid = [(1, 16, 48), (1, 16, 64), (1, 16, 96), (1, 16, 128), (1, 8, 64), (2, 16, 64), (2, 16, 96), (4, 16, 96)]
                 else:
-                    grid = [(1, 8, 48), (1, 16, 32), (1, 16, 48), (1, 16, 64), (1, 16, 96), (1, 32, 64), (2, 16, 48), (2, 16, 64),
-                            (4, 16, 64)]
+                    grid = [(1, 16, 64), (2, 16, 64), (4, 16, 64), (4, 16, 32), (4, 8, 64), (4, 16, 96), (8, 16, 64), (8, 16, 32)]
                 if args.quick and vname != 'push':
                     grid = grid[1:4]
                 for chunk_mib, copy, red in grid:

@@ -133,13 +133,13 @@ def test_pipelined_allreduce_out_of_place_and_back_to_back(pipe_groups, world):
 
 
 def test_auto_picks_the_pipeline_for_large_aligned_messages(pipe_groups):
-    """AUTO: ordinary 16-byte aligned tensors from 8 MiB on go through the pipelined kernels
-    (push at world 2); a misaligned view of the same size falls back to the staged kernels and
+    """AUTO: ordinary 16-byte aligned tensors from 16 MiB on go through the pipelined kernels
+    (pull at world 2); a misaligned view of the same size falls back to the staged kernels and
     still produces the same bits."""
     from ray_b200 import _native as N
 
     g = pipe_groups(2)
-    numel = (12 * MiB) // 4
+    numel = (20 * MiB) // 4
     host = [_rand(numel + 1, torch.float32, 5 + r) for r in range(2)]
     want = O.reduce_rank_ascending([h[:numel].numpy() for h in host], N.SUM)
     xs = [h.to(g.device(r)) for r, h in enumerate(host)]
@@ -173,7 +173,13 @@ def test_pipeline_tuning_parameters_do_not_change_results(pipe_groups, world):
             xs = [h.to(g.device(r)) for r, h in enumerate(host)]
             g.run(lambda c, r: c.allreduce(xs[r], N.SUM, algo=N.ALGO_PIPE))
             for r in range(world):
-                assert np.array_equal(xs[r].cpu().numpy(), want), (world, chunk, copy_ctas, red_ctas)
+                got = xs[r].cpu().numpy()
+                if g.has_multicast and world > 2:  # NVLS roles: the switch picks the summation order
+                    bound = 1e-6 * np.sum([np.abs(h.numpy().astype(np.float64)) for h in host], axis=0)
+                    assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= bound)
+                    assert np.array_equal(got, xs[0].cpu().numpy())
+                else:
+                    assert np.array_equal(got, want), (world, chunk, copy_ctas, red_ctas)
     finally:
         for c in g.comms:
             for p in (N.PARAM_PIPE_CHUNK_BYTES, N.PARAM_PIPE_COPY_CTAS, N.PARAM_PIPE_RED_CTAS):
