@@ -50,6 +50,7 @@ def parse_args():
                    help="wire dtype of the fused gradient hook; none = plain reducer all-reduce")
     p.add_argument("--no-sweep", action="store_true", help="skip the all-reduce bandwidth sweep (N>1)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-nccl-comparator", action="store_true", help="skip the in-line NCCL comparator leg (N>1)")
     p.add_argument("--profile", action="store_true",
                    help="under ncu: skip the end-to-end and sweep legs (numbers printed in this mode are not bench values)")
     p.add_argument("--cpu-worker", default=None, help=argparse.SUPPRESS)
@@ -230,9 +231,12 @@ def run_gpu(args):
     kernel_ms = []
     kernel_bytes = []
     if pg is not None:
-        for start, end, nbytes in pg.timings:
-            kernel_ms.append(start.elapsed_time(end))
-            kernel_bytes.append(nbytes)
+        # only the fused gradient-bucket launches ("grad"); DDP's per-forward buffer broadcasts and
+        # anything else that goes through the process group are not the roofline kernel
+        for start, end, nbytes, tag in pg.timings:
+            if tag == "grad":
+                kernel_ms.append(start.elapsed_time(end))
+                kernel_bytes.append(nbytes)
     log(f"device-timed: {ms / args.steps:.2f} ms/step; timing end-to-end (host batch in, loss out)")
     # end to end: host batch in, loss out, every step
     if args.profile:
@@ -291,10 +295,19 @@ def run_gpu(args):
                         "note": "in-step launches include waiting for the slowest rank's bucket"}
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
 
-    sweep = None
+    sweep = ag_sweep = parity = nccl_cmp = ppo = None
     if world > 1 and not args.no_sweep and not args.profile:
-        log("all-reduce bandwidth sweep")
-        sweep = allreduce_sweep(args, pg, rank, world, device)
+        if args.impl == "b200":
+            log("parity check against the gloo side of the process group (untimed)")
+            parity = parity_check(pg, rank, world, device)
+        log("all-reduce / all-gather bandwidth sweeps")
+        sweep = collective_sweep(args, pg, rank, world, device, "allreduce")
+        ag_sweep = collective_sweep(args, pg, rank, world, device, "allgather")
+        ppo = ppo_allreduce_latency(args, pg, rank, world, device)
+        if args.impl == "b200" and not args.no_nccl_comparator:
+            log("NCCL comparator: same sweeps and the same DDP step over a ProcessGroupNCCL (not the product)")
+            # free the product's model first: the comparator builds its own
+            nccl_cmp = nccl_comparator(args, rank, world, device, dev_x, dev_y, host_x, host_y, loss_host)
 
     line = None
     if rank == 0:
@@ -320,49 +333,277 @@ def run_gpu(args):
             line["roofline"] = roofline
         if sweep is not None:
             line["allreduce_sweep"] = sweep
+        if ag_sweep is not None:
+            line["allgather_sweep"] = ag_sweep
+        if ppo is not None:
+            line["ppo_mlp_allreduce"] = ppo
+        if parity is not None:
+            line["parity_check"] = parity
+        if nccl_cmp is not None:
+            line["nccl_comparator"] = nccl_cmp
     if world > 1:
         dist.barrier()
     dist.destroy_process_group()
     return line
 
 
-def allreduce_sweep(args, pg, rank, world, device):
-    """All-reduce bus bandwidth vs message size (nccl-tests convention: busbw = S/t * 2(n-1)/n).
-    In-place on fp32 tensors resident in HBM, 5 warm-up + 20 timed launches per size, CUDA
-    events, max over ranks."""
+def _time_collective(one, iters, world):
+    """5 warm-up + `iters` timed launches, CUDA events on the launching stream, max over ranks -> us."""
+    import torch
+    import torch.distributed as dist
+
+    for _ in range(5):
+        one()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(iters):
+        one()
+    t1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([t0.elapsed_time(t1) / iters], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)  # CPU tensor -> gloo
+    return float(t.item()) * 1e3
+
+
+def collective_sweep(args, pg, rank, world, device, op, group=None):
+    """Bus bandwidth vs message size, nccl-tests convention:
+      allreduce: S = tensor bytes, busbw = S/t * 2(n-1)/n, in place on an ordinary fp32 tensor;
+      allgather: S = total gathered bytes (n x per-rank), busbw = S/t * (n-1)/n.
+    `group` = a torch ProcessGroup to time instead of the product (the NCCL comparator)."""
     import torch
     import torch.distributed as dist
 
     out = []
     sizes = [1 << s for s in range(10, 31, 2)]  # 1 KiB .. 1 GiB
     for nbytes in sizes:
-        x = torch.ones(nbytes // 4, device=device)
         iters = 20 if nbytes <= (256 << 20) else 8
-
-        def one():
-            if args.impl == "b200":
-                pg.comm.allreduce(x)
+        if op == "allreduce":
+            x = torch.ones(nbytes // 4, device=device)
+            if group is None and args.impl == "b200":
+                one = lambda: pg.comm.allreduce(x)  # noqa: E731
             else:
-                dist.all_reduce(x)
+                one = lambda: dist.all_reduce(x, group=group)  # noqa: E731
+            factor = 2 * (world - 1) / world
+            bufs = (x,)
+        else:
+            per = max(nbytes // world // 4, 1)
+            x = torch.ones(per, device=device)
+            y = torch.empty(per * world, device=device)
+            if group is None and args.impl == "b200":
+                one = lambda: pg.comm.allgather_into(y, x)  # noqa: E731
+            else:
+                one = lambda: dist.all_gather_into_tensor(y, x, group=group)  # noqa: E731
+            factor = (world - 1) / world
+            nbytes = per * world * 4
+            bufs = (x, y)
+        us = _time_collective(one, iters, world)
+        algbw = nbytes / (us * 1e-6) / 1e9
+        out.append({"bytes": nbytes, "us": round(us, 2), "algbw_gbs": round(algbw, 2), "busbw_gbs": round(algbw * factor, 2)})
+        del bufs, x
+    return out
 
-        for _ in range(5):
-            one()
+
+def ppo_mlp_numel():
+    """RLlib's default PPO module (rllib/core/rl_module/default_model_config.py:65-69: two 256-wide
+    tanh layers, separate policy and value networks) on a CartPole-sized space (4 observations,
+    2 actions): the gradient vector a 4-learner LearnerGroup all-reduces every update
+    (BASELINE.json configs[3])."""
+    import torch.nn as nn
+
+    def mlp(out):
+        return nn.Sequential(nn.Linear(4, 256), nn.Tanh(), nn.Linear(256, 256), nn.Tanh(), nn.Linear(256, out))
+
+    return sum(p.numel() for m in (mlp(2), mlp(1)) for p in m.parameters())
+
+
+def ppo_allreduce_latency(args, pg, rank, world, device, group=None):
+    import torch
+    import torch.distributed as dist
+
+    numel = ppo_mlp_numel()
+    g = torch.ones(numel, device=device)
+    if group is None and args.impl == "b200":
+        one = lambda: pg.comm.allreduce(g)  # noqa: E731
+    else:
+        one = lambda: dist.all_reduce(g, group=group)  # noqa: E731
+    us = _time_collective(one, 200, world)
+    return {"numel": numel, "bytes": numel * 4, "us_per_allreduce": round(us, 2), "world": world,
+            "note": "fp32 gradient vector of RLlib's default PPO MLPs; BASELINE configs[3] is world 4"}
+
+
+def parity_check(pg, rank, world, device):
+    """Multi-GPU parity where the driver can see it: seeded inputs through the product kernels
+    (AUTO algorithm selection: NVLS / pipelined / staged as the size dictates), compared with the
+    gloo side of the SAME process group (the reference's CPU backend, torch_gloo_collective_group.py:
+    208-290) -- fp32 within 1e-6 * sum_r|x_r| (north_star), integers and copies bit exact, every
+    replica bit-identical.  Raises on the first mismatch; returns the summary for the JSON line."""
+    import torch
+    import torch.distributed as dist
+
+    comm = pg.comm
+    cases = failed = 0
+    max_rel = 0.0
+    detail = []
+
+    def seeded(numel, dtype, r, salt=0):
+        gen = torch.Generator().manual_seed(1234 + r + 1000 * salt)
+        if dtype.is_floating_point:
+            return torch.randn(numel, generator=gen).to(dtype)
+        return torch.randint(-1000, 1000, (numel,), generator=gen, dtype=dtype)
+
+    def replicas_identical(t):
+        v = t.view(torch.uint8).view(-1)
+        pad = (-v.numel()) % 8
+        if pad:
+            v = torch.cat([v, torch.zeros(pad, dtype=torch.uint8, device=v.device)])
+        w = v.view(torch.int64)
+        sig = torch.stack([w.sum(), (w ^ (w >> 7)).sum()]).cpu()
+        sigs = [torch.zeros_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)  # CPU -> gloo
+        return all(torch.equal(x, sigs[0]) for x in sigs)
+
+    def record(name, ok, rel=0.0):
+        nonlocal cases, failed, max_rel
+        cases += 1
+        max_rel = max(max_rel, float(rel))
+        if not ok:
+            failed += 1
+        detail.append({"case": name, "ok": bool(ok), "max_rel": float(rel)})
+
+    MiB = 1 << 20
+    # ---- all-reduce fp32 / bf16 / int32 ------------------------------------------------------
+    for dtype, sizes, tol in ((torch.float32, (1 * MiB, 64 * MiB, 256 * MiB), 1e-6), (torch.bfloat16, (1 * MiB, 64 * MiB), 2.0 ** -7),
+                              (torch.int32, (1 * MiB, 64 * MiB), 0.0)):
+        for nbytes in sizes:
+            numel = nbytes // torch.empty((), dtype=dtype).element_size()
+            host = seeded(numel, dtype, rank)
+            x = host.to(device)
+            comm.allreduce(x)
+            torch.cuda.synchronize()
+            got = x.cpu()
+            if dtype == torch.int32:
+                ref = host.clone()
+                dist.all_reduce(ref)  # gloo
+                ok = torch.equal(got, ref)
+                rel = 0.0
+            else:
+                ref = host.float()
+                dist.all_reduce(ref)
+                sabs = host.float().abs()
+                dist.all_reduce(sabs)
+                err = (got.float() - (ref if dtype == torch.float32 else ref.to(dtype).float())).abs()
+                rel = float((err / sabs.clamp_min(1e-30)).max())
+                ok = bool((err <= tol * sabs + 1e-30).all())
+            ok = ok and replicas_identical(x)
+            record(f"allreduce/{str(dtype)[6:]}/{nbytes >> 20}MiB", ok, rel)
+            del x, got, ref
+    # ---- fused gradient kernel (fp32 bucket, bf16 wire, scale 1/world) ------------------------
+    numel = 25 * MiB // 4
+    host = seeded(numel, torch.float32, rank, salt=1)
+    gbuf = host.to(device)
+    comm.grad_allreduce(gbuf, 1.0 / world, torch.bfloat16)
+    torch.cuda.synchronize()
+    wire = (host * (1.0 / world)).to(torch.bfloat16).float()
+    ref = wire.clone()
+    dist.all_reduce(ref)
+    sabs = wire.abs()
+    dist.all_reduce(sabs)
+    err = (gbuf.cpu() - ref.to(torch.bfloat16).float()).abs()
+    rel = float((err / sabs.clamp_min(1e-30)).max())
+    record("grad_allreduce/bf16wire/25MiB", bool((err <= 2.0 ** -7 * sabs + 1e-30).all()) and replicas_identical(gbuf), rel)
+    del gbuf
+    # ---- all-gather, reduce-scatter, broadcast (64 MiB total / per op) ------------------------
+    per = 64 * MiB // 4 // world
+    x = seeded(per, torch.float32, rank, salt=2).to(device)
+    y = torch.empty(per * world, device=device)
+    comm.allgather_into(y, x)
+    torch.cuda.synchronize()
+    want = torch.cat([seeded(per, torch.float32, p, salt=2) for p in range(world)])
+    record("allgather/f32/64MiB", torch.equal(y.cpu(), want))
+    full = seeded(per * world, torch.float32, rank, salt=3)
+    out = torch.empty(per, device=device)
+    comm.reducescatter_from(out, full.to(device))
+    torch.cuda.synchronize()
+    ref = full.clone()
+    dist.all_reduce(ref)  # the reference's gloo reducescatter is n all-reduces (torch_gloo_collective_group.py:260-282)
+    sabs = full.abs()
+    dist.all_reduce(sabs)
+    sl = slice(rank * per, (rank + 1) * per)
+    err = (out.cpu() - ref[sl]).abs()
+    rel = float((err / sabs[sl].clamp_min(1e-30)).max())
+    record("reducescatter/f32/64MiB", bool((err <= 1e-6 * sabs[sl] + 1e-30).all()), rel)
+    root = world - 1
+    b = seeded(16 * MiB // 4, torch.float32, rank, salt=4).to(device)
+    comm.broadcast(b, root)
+    torch.cuda.synchronize()
+    record("broadcast/f32/16MiB", torch.equal(b.cpu(), seeded(16 * MiB // 4, torch.float32, root, salt=4)))
+    # every rank must agree that nothing failed
+    flag = torch.tensor([failed], dtype=torch.int64)
+    dist.all_reduce(flag)
+    summary = {"cases": cases, "failed": int(flag.item()), "max_rel": max_rel, "multicast": bool(comm.has_multicast),
+               "tolerance": "fp32 1e-6*sum|x_r| vs gloo; bf16 2^-7*sum|x_r| (one rounding of an fp32 sum); int/copies bit exact; "
+                            "replicas bit-identical", "detail": detail}
+    if summary["failed"]:
+        raise RuntimeError(f"parity check failed: {json.dumps(summary)}")
+    return summary
+
+
+def nccl_comparator(args, rank, world, device, dev_x, dev_y, host_x, host_y, loss_host):
+    """The reference's GPU backend is NCCL (nccl_collective_group.py / torch c10d); the reference
+    itself cannot run here (no Ray, no cupy), so the comparator is torch's ProcessGroupNCCL on the
+    same box, in the same processes: the same sweeps and the same DDP step with bf16_compress_hook."""
+    import torch
+    import torch.distributed as dist
+    from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    nccl = dist.new_group(backend="nccl")
+    fake_args = argparse.Namespace(impl="nccl")
+    out = {"backend": f"torch ProcessGroupNCCL, NCCL {'.'.join(map(str, torch.cuda.nccl.version()))}",
+           "allreduce_sweep": collective_sweep(fake_args, None, rank, world, device, "allreduce", group=nccl),
+           "allgather_sweep": collective_sweep(fake_args, None, rank, world, device, "allgather", group=nccl),
+           "ppo_mlp_allreduce": ppo_allreduce_latency(fake_args, None, rank, world, device, group=nccl)}
+    model = DDP(build(device), device_ids=[device], output_device=device, process_group=nccl)
+    if args.grad_wire == "bf16":
+        model.register_comm_hook(nccl, default_hooks.bf16_compress_hook)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+    def timed(steps, resident):
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
-        for _ in range(iters):
-            one()
+        for _ in range(steps):
+            if resident:
+                x, y = dev_x, dev_y
+            else:
+                x = host_x.to(device, non_blocking=True)
+                y = host_y.to(device, non_blocking=True)
+            loss = train_step(model, opt, x, y, "cuda")
+            if not resident:
+                loss_host.copy_(loss.detach().float(), non_blocking=True)
         t1.record()
         torch.cuda.synchronize()
-        t = torch.tensor([t0.elapsed_time(t1) / iters], dtype=torch.float64)
+        t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        us = float(t.item()) * 1e3
-        algbw = nbytes / (us * 1e-6) / 1e9
-        out.append({"bytes": nbytes, "us": round(us, 2), "algbw_gbs": round(algbw, 2),
-                    "busbw_gbs": round(algbw * 2 * (world - 1) / world, 2)})
-        del x
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 5)):  # NCCL connects lazily and autotunes in its first steps
+        train_step(model, opt, dev_x, dev_y, "cuda")
+    timed(2, False)
+    B = dev_x.shape[0]
+    ms = timed(args.steps, True)
+    ms_e2e = timed(args.steps, False)
+    out["samples_s"] = B * world * args.steps / (ms / 1e3)
+    out["e2e_samples_s"] = B * world * args.steps / (ms_e2e / 1e3)
+    out["ms_per_step"] = ms / args.steps
+    out["grad_sync"] = "torch DDP + NCCL" + (" bf16_compress_hook" if args.grad_wire == "bf16" else "")
+    del model, opt
+    torch.cuda.empty_cache()
     return out
 
 

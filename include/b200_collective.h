@@ -90,7 +90,7 @@ typedef struct {
   size_t heap_bytes;    /* symmetric user heap for zero-copy operands (0 -> none) */
   size_t inbox_bytes;   /* per-peer point-to-point inbox (0 -> default 32 MiB) */
   int enable_multicast; /* 1: try to create the NVLS multicast mapping, 0: never */
-  int timeout_ms;       /* device-side watchdog for peer waits (0 -> default 30000) */
+  int timeout_ms;       /* device-side watchdog for peer waits (0 -> default 600000 = 10 min) */
 } b200_config_t;
 
 /* ---- lifecycle / bootstrap ------------------------------------------------

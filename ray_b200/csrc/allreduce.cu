@@ -346,8 +346,13 @@ extern "C" int b200_allreduce(b200_comm_t c, const void *in, void *out, size_t c
   }
 
   // zero-copy when the operand sits in the symmetric heap (and is updated in place)
+  // The reduce phase works on whole 16-byte units straight in the heap, so a tensor whose size is
+  // not a multiple of 16 bytes would have the bytes that follow it reduced as well: such operands
+  // take the staged path (which zero-pads the tail unit in the slot instead).  Every rank must pass
+  // the tensor at the same heap offset (b200_symm_alloc / the pool hand out identical offsets when
+  // ranks allocate in the same order, which both interfaces require).
   long long sym_off = -1;
-  if (in == out && b200_symm_contains(c, in, total) && is_aligned16(in))
+  if (in == out && (total & 15) == 0 && b200_symm_contains(c, in, total) && is_aligned16(in))
     sym_off = static_cast<const char *>(in) - reinterpret_cast<const char *>(c->data.va[c->rank]);
 
   const char *src = static_cast<const char *>(in);

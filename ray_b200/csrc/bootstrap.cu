@@ -429,6 +429,18 @@ int check_usable(b200_comm *c) {
     set_error("communicator is not connected (call b200_comm_connect first)");
     return B200_ERR_INVALID;
   }
+  // A kernel that gave up (watchdog / abort) leaves the flag protocol in an undefined state: the
+  // launch counter still advanced, peers may be mid-collective.  Treat it as fatal for the
+  // communicator -- later launches are refused instead of running against stale flags.
+  if (c->h_abort) {
+    const int st = __atomic_load_n(&c->h_abort[1], __ATOMIC_ACQUIRE);
+    if (st != 0) {
+      set_error(st == B200_ERR_TIMEOUT ? "a previous collective timed out waiting for a peer (device watchdog); "
+                                         "the communicator is unusable"
+                                       : "a previous collective was aborted; the communicator is unusable");
+      return st;
+    }
+  }
   return B200_OK;
 }
 
@@ -497,7 +509,9 @@ int b200_comm_create(int world_size, int rank, int device, const b200_config_t *
   else c->cfg.enable_multicast = 1;
   if (c->cfg.staging_bytes == 0) c->cfg.staging_bytes = size_t(256) << 20;
   if (c->cfg.inbox_bytes == 0) c->cfg.inbox_bytes = size_t(32) << 20;
-  if (c->cfg.timeout_ms <= 0) c->cfg.timeout_ms = 30000;
+  // device watchdog: minutes, not seconds -- a rank may legitimately be late by a checkpoint, an
+  // evaluation pass or a first-step compile (c10d's default collective timeout is 10-30 minutes)
+  if (c->cfg.timeout_ms <= 0) c->cfg.timeout_ms = 600000;
 
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {

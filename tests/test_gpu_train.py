@@ -128,3 +128,138 @@ def test_c10d_backend_and_ddp_gradient_path(native_lib, wire):
         mp.spawn(_worker, args=(world, init_file, d, wire), nprocs=world, join=True)
         launches = [int(open(os.path.join(d, f"ok{r}")).read()) for r in range(world)]
         assert all(l > 0 for l in launches), "no native kernels were launched"
+
+
+def _fsdp_worker(rank, world, init_file, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import torch.nn as nn
+    from torch.distributed.fsdp import FullyShardedDataParallel as FSDP
+
+    from ray_b200 import train as T
+
+    ndev = torch.cuda.device_count()
+    os.environ["LOCAL_RANK"] = str(rank if ndev >= world else 0)
+    device = T.get_device()
+    torch.cuda.set_device(device)
+    T.setup_torch_process_group(T.DEFAULT_GPU_BACKEND, rank, world, f"file://{init_file}", timeout_s=120)
+    pg = dist.distributed_c10d._get_default_group()
+    if ndev < world:
+        x = torch.zeros(1, device=device)
+        dist.all_reduce(x)
+        pg.comm.set_blocks(32)
+
+    # --- rooted and all-to-all ops of the c10d surface ------------------------------------------
+    mine = torch.full((5,), float(rank + 1), device=device)
+    outs = [torch.zeros(5, device=device) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, outs, dst=0)
+    if rank == 0:
+        assert all(torch.all(outs[p] == p + 1) for p in range(world))
+    got = torch.zeros(3, device=device)
+    dist.scatter(got, [torch.full((3,), 10.0 * p, device=device) for p in range(world)] if rank == 1 else None, src=1)
+    assert torch.all(got == 10.0 * rank)
+    src = torch.arange(4 * world, device=device, dtype=torch.float32) + 100 * rank
+    dst = torch.zeros(4 * world, device=device)
+    dist.all_to_all_single(dst, src)
+    want = torch.cat([torch.arange(4 * rank, 4 * rank + 4, dtype=torch.float32) + 100 * p for p in range(world)])
+    assert torch.equal(dst.cpu(), want)
+    big_src = torch.randn(world * (3 << 20), device=device)  # 12 MiB per peer: larger than the eager ring
+    big_dst = torch.zeros_like(big_src)
+    dist.all_to_all_single(big_dst, big_src)
+    gathered = [torch.empty_like(big_src) for _ in range(world)]
+    dist.all_gather(gathered, big_src)
+    n = 3 << 20
+    for p in range(world):
+        assert torch.equal(big_dst[p * n:(p + 1) * n], gathered[p][rank * n:(rank + 1) * n])
+    work = dist.all_reduce(mine, async_op=True)
+    work.wait()
+    torch.cuda.synchronize()
+    assert work.is_completed() and work.is_success() and work.exception() is None
+
+    # --- FSDP through prepare_model(parallel_strategy="fsdp") (train_loop_utils.py:153-190) -------
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(32, 64), nn.ReLU(), nn.Linear(64, 8))
+    ref = nn.Sequential(nn.Linear(32, 64), nn.ReLU(), nn.Linear(64, 8)).to(device)
+    ref.load_state_dict(model.state_dict())
+    fsdp = T.prepare_model(model, parallel_strategy="fsdp")
+    assert isinstance(fsdp, FSDP)
+    opt = torch.optim.SGD(fsdp.parameters(), lr=0.1)
+    ref_opt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    loss_fn = nn.MSELoss()
+    for step in range(3):
+        xs = [torch.randn(8, 32, generator=torch.Generator().manual_seed(10 * step + r)).to(device) for r in range(world)]
+        ys = [torch.randn(8, 8, generator=torch.Generator().manual_seed(50 * step + r)).to(device) for r in range(world)]
+        loss_fn(fsdp(xs[rank]), ys[rank]).backward()
+        opt.step()
+        opt.zero_grad()
+        ref.zero_grad()
+        sum(loss_fn(ref(xs[r]), ys[r]) for r in range(world)).div(world).backward()
+        ref_opt.step()
+        with FSDP.summon_full_params(fsdp):
+            for (n1, p1), (_, p2) in zip(fsdp.module.named_parameters(), ref.named_parameters()):
+                assert torch.allclose(p1, p2, atol=1e-5, rtol=1e-5), (step, n1, (p1 - p2).abs().max().item())
+    launches = pg.comm.launch_count
+    torch.cuda.synchronize()
+    pg.comm.check_status()
+    dist.barrier()
+    dist.destroy_process_group()
+    with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+        f.write(str(launches))
+
+
+def test_c10d_rooted_ops_work_semantics_and_fsdp(native_lib):
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_fsdp_worker, args=(world, os.path.join(d, "rdzv"), d), nprocs=world, join=True)
+        assert all(int(open(os.path.join(d, f"ok{r}")).read()) > 0 for r in range(world))
+
+
+def _late_rank_worker(rank, world, init_file, out_dir):
+    """Rank 1 never joins the collective: rank 0's watchdog must surface as an exception through
+    Work.wait(timeout) / barrier, and later launches must be refused (a timed-out
+    kernel used to leave unreduced gradients with nobody told)."""
+    sys.path.insert(0, ROOT)
+    import time
+
+    import torch.distributed as dist
+
+    from ray_b200 import _native as N
+    from ray_b200 import train as T
+
+    ndev = torch.cuda.device_count()
+    os.environ["LOCAL_RANK"] = str(rank if ndev >= world else 0)
+    device = T.get_device()
+    torch.cuda.set_device(device)
+    T.setup_torch_process_group(T.DEFAULT_GPU_BACKEND, rank, world, f"file://{init_file}", timeout_s=2)
+    x = torch.ones(10, device=device)
+    dist.all_reduce(x)  # both ranks: creates the communicator (watchdog = the 2 s group timeout)
+    torch.cuda.synchronize()
+    ok = "skipped"
+    if rank == 0:
+        work = dist.all_reduce(x, async_op=True)  # rank 1 never issues this one
+        t0 = time.time()
+        try:
+            work.wait(__import__("datetime").timedelta(seconds=30))
+            torch.cuda.synchronize()
+            ok = "no exception" if work.is_success() else "flagged"
+        except N.B200Error:
+            ok = "raised"
+        assert time.time() - t0 < 20
+        assert not work.is_success() and work.exception() is not None
+        try:
+            dist.all_reduce(x)
+            ok = "later launch accepted"
+        except N.B200Error:
+            pass
+    else:
+        time.sleep(6)
+    with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+        f.write(ok)
+    os._exit(0)  # the group is broken by design: skip the collective teardown
+
+
+def test_late_rank_surfaces_as_an_error_not_silent_divergence(native_lib):
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_late_rank_worker, args=(world, os.path.join(d, "rdzv"), d), nprocs=world, join=True)
+        assert open(os.path.join(d, "ok0")).read() in ("raised", "flagged")
