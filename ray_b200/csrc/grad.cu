@@ -177,11 +177,12 @@ static int launch_grad(b200_comm *c, GradArgs a, cudaStream_t stream) {
   if (c->world == 1) {
     // units per thread: tuning knob, default measured on B200 (profiles/r02/grad_local_sweep.txt)
     const long long unr = c->params[B200_PARAM_GRAD_LOCAL_UNROLL];
-    switch (unr > 0 ? int(unr) : 2) {
+    switch (unr > 0 ? int(unr) : 1) {
       case 1: launch_grad_local<W, 1>(a, U, stream); break;
       case 4: launch_grad_local<W, 4>(a, U, stream); break;
       case 8: launch_grad_local<W, 8>(a, U, stream); break;
-      default: launch_grad_local<W, 2>(a, U, stream); break;
+      case 2: launch_grad_local<W, 2>(a, U, stream); break;
+      default: launch_grad_local<W, 1>(a, U, stream); break;
     }
     B200_LAUNCH_CHECK(c);
     return B200_OK;
