@@ -120,7 +120,13 @@ class B200Communicator(Communicator):
     def __init__(self, world_size: int, comm_id: Optional[str] = None, rank: Optional[int] = None,
                  actor_handles: Optional[list] = None, cuda_stream: Optional[torch.cuda.Stream] = None,
                  use_communication_streams: bool = False, store: Optional[Store] = None,
-                 device: Optional[int] = None, **comm_kwargs):
+                 device: Optional[int] = None, host_sync: bool = False, **comm_kwargs):
+        #: False (default): no host synchronisation per op.  Every op is enqueued and the tensor it
+        #: produces is guarded by a CUDA event that the caller's current stream waits on -- the
+        #: GPUFuture contract of the reference's overlap mode (dag/dag_operation_future.py:101-133,
+        #: nccl_group.py:168-174) applied to every mode.  True: block the host after every recv /
+        #: collective like the reference's non-overlap path (nccl_group.py:232-240,262-266).
+        self._host_sync = host_sync
         self._world_size = world_size
         self._comm_id = comm_id or self.generate_communicator_id()
         self._rank: Optional[int] = None
@@ -139,12 +145,14 @@ class B200Communicator(Communicator):
     # pickling: only the description travels, never the native handle
     def __getstate__(self):
         return {"world_size": self._world_size, "comm_id": self._comm_id, "actor_handles": self._actor_handles,
-                "use_communication_streams": self._use_communication_streams, "comm_kwargs": self._comm_kwargs,
+                "use_communication_streams": self._use_communication_streams, "host_sync": self._host_sync,
+                "comm_kwargs": self._comm_kwargs,
                 "store": self._store if _is_picklable_store(self._store) else None}
 
     def __setstate__(self, st):
         self.__init__(st["world_size"], st["comm_id"], None, st["actor_handles"], None,
-                      st["use_communication_streams"], st.get("store"), None, **st.get("comm_kwargs", {}))
+                      st["use_communication_streams"], st.get("store"), None, st.get("host_sync", False),
+                      **st.get("comm_kwargs", {}))
 
     # ------------------------------------------------------------------ membership
     def initialize(self, rank: int) -> None:
@@ -191,11 +199,22 @@ class B200Communicator(Communicator):
             raise RayChannelError(what)
         return self._comm
 
+    def _raise_if_failed(self, comm: B200Comm, what: str = "B200 group has been destroyed.") -> None:
+        """Non-blocking health check: the kernels mirror their sticky status into host-mapped memory,
+        so this is a plain load -- no CUDA call, no synchronisation."""
+        if self._closed or comm.status() != 0:
+            raise RayChannelError(what)
+
     def send(self, buf: torch.Tensor, peer_rank: int) -> None:
         comm = self._check_open()
-        if self._use_communication_streams:
-            self._send_stream.synchronize()  # keep the host loop from running far ahead (nccl_group.py:167-174)
+        self._raise_if_failed(comm)
         try:
+            cur = torch.cuda.current_stream(self._device)
+            if self._send_stream is not cur and self._send_stream.cuda_stream != cur.cuda_stream:
+                # the tensor was produced on the caller's stream: order the send after it on the
+                # device (the reference blocks the host here instead, nccl_group.py:167-174)
+                self._send_stream.wait_stream(cur)
+                buf.record_stream(self._send_stream)
             comm.send(buf, peer_rank, stream=self._send_stream)
         except N.B200AbortedError as e:
             raise RayChannelError(str(e)) from e
@@ -204,23 +223,44 @@ class B200Communicator(Communicator):
              allocator: Optional[TorchTensorAllocator] = None) -> torch.Tensor:
         comm = self._check_open()
         assert allocator is not None, "B200 group requires a tensor allocator"
+        self._raise_if_failed(comm)
         buf = allocator(shape, dtype)
         try:
-            if self._use_communication_streams:
-                self._recv_stream.synchronize()
-                comm.recv(buf, peer_rank, stream=self._recv_stream)
-            else:
-                comm.recv(buf, peer_rank, stream=self._recv_stream)
+            cur = torch.cuda.current_stream(self._device)
+            same = self._recv_stream is cur or self._recv_stream.cuda_stream == cur.cuda_stream
+            if not same:
+                self._recv_stream.wait_stream(cur)  # the allocation may recycle memory still in use on `cur`
+                buf.record_stream(self._recv_stream)
+            comm.recv(buf, peer_rank, stream=self._recv_stream)
+            if self._host_sync:
                 # Buffer contents are undefined if the op was aborted: wait and re-check
                 # (nccl_group.py:232-240).
                 self._recv_stream.synchronize()
-                if self._closed or comm.status() != 0:
-                    raise RayChannelError("B200 group has been destroyed.")
+                self._raise_if_failed(comm)
+            else:
+                ev = torch.cuda.Event()
+                ev.record(self._recv_stream)
+                if not same:
+                    cur.wait_event(ev)  # safe to read on the caller's stream; other streams wait on the event
+                buf._b200_ready = ev  # noqa: SLF001 - the GPUFuture-style handle of this tensor
+                self._last_recv_event = ev
         except N.B200AbortedError as e:
             raise RayChannelError(str(e)) from e
         if self._closed:
             raise RayChannelError("B200 group has been destroyed.")
         return buf
+
+    def wait(self, tensor: Optional[torch.Tensor] = None) -> None:
+        """Block the host until ``tensor`` (default: the most recent recv) has arrived, then raise
+        ``RayChannelError`` if the group was destroyed / aborted meanwhile -- what the reference's
+        non-overlap recv does implicitly on every call."""
+        ev = getattr(tensor, "_b200_ready", None) if tensor is not None else getattr(self, "_last_recv_event", None)
+        if ev is not None:
+            ev.synchronize()
+        if self._comm is not None:
+            self._raise_if_failed(self._comm)
+        elif self._closed:
+            raise RayChannelError("B200 group has been destroyed.")
 
     @property
     def recv_stream(self):
@@ -236,13 +276,23 @@ class B200Communicator(Communicator):
         assert send_buf.dtype == recv_buf.dtype, (
             "Ray Compiled Graph derived the dtype of recv_buf from send_buf, so send_buf and recv_buf must "
             "have the same dtype.")
+        what = ("B200 group has been destroyed during a collective operation. There may "
+                "be a dtype mismatch between input tensors from different ranks.")
+        self._raise_if_failed(comm, what)
         try:
+            cur = torch.cuda.current_stream(self._device)
+            same = self._cuda_stream is cur or self._cuda_stream.cuda_stream == cur.cuda_stream
+            if not same:
+                self._cuda_stream.wait_stream(cur)
             with torch.cuda.stream(self._cuda_stream):
                 fn(comm)
-            self._cuda_stream.synchronize()  # nccl_group.py:262-266
-            if self._closed or comm.status() != 0:
-                raise RayChannelError("B200 group has been destroyed during a collective operation. There may "
-                                      "be a dtype mismatch between input tensors from different ranks.")
+            if self._host_sync:
+                self._cuda_stream.synchronize()  # nccl_group.py:262-266
+                self._raise_if_failed(comm, what)
+            elif not same:
+                cur.wait_stream(self._cuda_stream)  # device-side ordering only
+                send_buf.record_stream(self._cuda_stream)
+                recv_buf.record_stream(self._cuda_stream)
         except N.B200AbortedError as e:
             raise RayChannelError(str(e)) from e
 
@@ -264,16 +314,29 @@ class B200Communicator(Communicator):
         comm = self._check_open()
         if len({t.dtype for t in tensors}) > 1:
             raise ValueError(f"Expected all input tensors to have the same dtype, but got {[t.dtype for t in tensors]}")
+        self._raise_if_failed(comm)
         try:
+            cur = torch.cuda.current_stream(self._device)
+            same = self._cuda_stream is cur or self._cuda_stream.cuda_stream == cur.cuda_stream
+            if not same:
+                self._cuda_stream.wait_stream(cur)
             with torch.cuda.stream(self._cuda_stream):
                 comm.allreduce_multi(list(tensors), code)
-            self._cuda_stream.synchronize()
-            if self._closed or comm.status() != 0:
-                raise RayChannelError("B200 group has been destroyed during a collective operation.")
+            if self._host_sync:
+                self._cuda_stream.synchronize()
+                self._raise_if_failed(comm, "B200 group has been destroyed during a collective operation.")
+            elif not same:
+                cur.wait_stream(self._cuda_stream)
         except N.B200AbortedError as e:
             raise RayChannelError(str(e)) from e
 
     # ------------------------------------------------------------------ lifecycle
+    def broadcast(self, tensor: torch.Tensor, root_rank: int) -> None:
+        """In-place broadcast over the WHOLE group (NVLS multimem.st when the multicast mapping
+        exists): the multi-reader fast path of the tensor channel -- the reference loops send per
+        reader and carries a TODO for exactly this (torch_tensor_accelerator_channel.py:587-590)."""
+        self._collective(tensor, tensor, lambda c: c.broadcast(tensor, root_rank))
+
     def destroy(self) -> None:
         if self._closed:
             return

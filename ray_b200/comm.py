@@ -295,6 +295,20 @@ class B200Comm:
         if st:
             N.check(st)
 
+    def send_ptr(self, ptr: int, nbytes: int, peer: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """send() from a raw device-visible address (e.g. pinned host memory under unified
+        addressing: the Compiled-Graph channel keeps its metadata header there)."""
+        st = self._lib.b200_send(self._h, ptr, int(nbytes), int(peer),
+                                 stream.cuda_stream if stream is not None else self._stream())
+        if st:
+            N.check(st)
+
+    def recv_ptr(self, ptr: int, nbytes: int, peer: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+        st = self._lib.b200_recv(self._h, ptr, int(nbytes), int(peer),
+                                 stream.cuda_stream if stream is not None else self._stream())
+        if st:
+            N.check(st)
+
     def grad_allreduce(self, grad: torch.Tensor, scale: float, wire_dtype: torch.dtype = torch.bfloat16) -> None:
         """Fused ``grad = sum_r wire(grad_r * scale)`` on a flat fp32 bucket."""
         _check_cuda_contiguous(grad)

@@ -10,6 +10,8 @@
 //   stage-out: read the reduced wire values, cast back to fp32, write the bucket
 //
 // With wire = bf16 the NVLink traffic and the staging traffic are halved.
+#include <type_traits>
+
 #include "allreduce_core.cuh"
 
 namespace b200 {
@@ -144,30 +146,67 @@ __global__ void __launch_bounds__(kThreads, 1) grad_allreduce_kernel(DevComm c, 
 // no flag rows are involved, so the grid is NOT clamped to kMaxBlocks (round-1 ran this kernel
 // at 43 % occupancy because of that clamp).
 constexpr int kLocalThreads = 256;
+// One thread = UNR x 16 bytes of the fp32 bucket (4 elements), whatever the wire type: nothing is
+// stored in wire format here, so the 8-element wire units of the multi-rank kernels would only
+// halve the thread count (ncu, 60 MB bucket: 20.0 us with 8-element units, 15.1 us with 4).
+template <typename W>
+__device__ __forceinline__ uint4 wire_round_trip(uint4 v, float scale) {
+  float f[4] = {__uint_as_float(v.x) * scale, __uint_as_float(v.y) * scale, __uint_as_float(v.z) * scale,
+                __uint_as_float(v.w) * scale};
+  if constexpr (std::is_same<W, __nv_bfloat16>::value) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
+  } else if constexpr (std::is_same<W, __half>::value) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = __half2float(__float2half_rn(f[i]));
+  }
+  return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+}
+
 template <typename W, int UNR>
 __global__ void __launch_bounds__(kLocalThreads) grad_local_kernel(GradArgs a) {
-  constexpr int E = Wire<W>::kElems;
-  const size_t U = (a.count + E - 1) / E;
-  const bool al = is_aligned16(a.grad);
+  const size_t U = a.count >> 2;  // whole 16-byte units; the host sends the ragged tail separately
   const size_t u0 = size_t(blockIdx.x) * kLocalThreads * UNR + threadIdx.x;
+  uint4 *g = reinterpret_cast<uint4 *>(a.grad);
   uint4 w[UNR];
 #pragma unroll
   for (int k = 0; k < UNR; ++k) {
     const size_t u = u0 + size_t(k) * kLocalThreads;
-    if (u < U) w[k] = load_grad_unit<W>(a.grad, u, a.count, a.scale, al);
+    if (u < U) w[k] = ld_stream(g + u);
   }
 #pragma unroll
   for (int k = 0; k < UNR; ++k) {
     const size_t u = u0 + size_t(k) * kLocalThreads;
-    if (u < U) store_grad_unit<W>(a.grad, u, a.count, al, w[k]);
+    if (u < U) st_vec(g + u, wire_round_trip<W>(w[k], a.scale));
+  }
+}
+
+// unaligned buckets / the last count % 4 elements
+template <typename W>
+__global__ void grad_local_scalar_kernel(GradArgs a) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < a.count; i += size_t(gridDim.x) * blockDim.x) {
+    float f = a.grad[i] * a.scale;
+    if constexpr (std::is_same<W, __nv_bfloat16>::value) f = __bfloat162float(__float2bfloat16_rn(f));
+    else if constexpr (std::is_same<W, __half>::value) f = __half2float(__float2half_rn(f));
+    a.grad[i] = f;
   }
 }
 
 template <typename W, int UNR>
-static void launch_grad_local(const GradArgs &a, size_t U, cudaStream_t stream) {
+static void launch_grad_local(const GradArgs &a, cudaStream_t stream) {
+  if (!is_aligned16(a.grad)) {
+    grad_local_scalar_kernel<W><<<1184, 256, 0, stream>>>(a);
+    return;
+  }
+  const size_t U = a.count >> 2;
   const size_t per_cta = size_t(kLocalThreads) * UNR;
-  const size_t g = (U + per_cta - 1) / per_cta;
-  grad_local_kernel<W, UNR><<<unsigned(g), kLocalThreads, 0, stream>>>(a);
+  if (U) grad_local_kernel<W, UNR><<<unsigned((U + per_cta - 1) / per_cta), kLocalThreads, 0, stream>>>(a);
+  if (a.count & 3) {
+    GradArgs tail = a;
+    tail.grad = a.grad + (U << 2);
+    tail.count = a.count & 3;
+    grad_local_scalar_kernel<W><<<1, 32, 0, stream>>>(tail);
+  }
 }
 
 template <typename W>
@@ -178,11 +217,10 @@ static int launch_grad(b200_comm *c, GradArgs a, cudaStream_t stream) {
     // units per thread: tuning knob, default measured on B200 (profiles/r02/grad_local_sweep.txt)
     const long long unr = c->params[B200_PARAM_GRAD_LOCAL_UNROLL];
     switch (unr > 0 ? int(unr) : 1) {
-      case 1: launch_grad_local<W, 1>(a, U, stream); break;
-      case 4: launch_grad_local<W, 4>(a, U, stream); break;
-      case 8: launch_grad_local<W, 8>(a, U, stream); break;
-      case 2: launch_grad_local<W, 2>(a, U, stream); break;
-      default: launch_grad_local<W, 1>(a, U, stream); break;
+      case 2: launch_grad_local<W, 2>(a, stream); break;
+      case 4: launch_grad_local<W, 4>(a, stream); break;
+      case 8: launch_grad_local<W, 8>(a, stream); break;
+      default: launch_grad_local<W, 1>(a, stream); break;
     }
     B200_LAUNCH_CHECK(c);
     return B200_OK;

@@ -38,7 +38,7 @@ def test_communicator_bookkeeping_and_pickle_without_gpu():
 def test_metadata_header_roundtrip(shape, dtype):
     t = torch.zeros(shape, dtype=dtype)
     raw = tc._encode(t)
-    assert len(raw) == tc._HEADER_BYTES
+    assert len(raw) == tc._DESC_BYTES
     got_shape, got_dtype = tc._decode(raw)
     assert tuple(got_shape) == tuple(shape) and got_dtype == dtype
     with pytest.raises(RayChannelError):

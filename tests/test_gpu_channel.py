@@ -222,11 +222,14 @@ def test_tensor_channel_dynamic_static_direct(actors):
         st[0].write([1, 2, 3])
 
 
-def test_destroy_from_another_thread_unblocks_recv_and_raises(actors):
-    """compiled_dag_node.py:2157-2199 teardown: destroy() while the reader sits in recv."""
+@pytest.mark.parametrize("host_sync", [False, True])
+def test_destroy_from_another_thread_unblocks_recv_and_raises(actors, host_sync):
+    """compiled_dag_node.py:2157-2199 teardown: destroy() while the reader waits for data.  With
+    host_sync=True the reader sits inside recv() like the reference's _NcclGroup; in the default
+    event mode recv() returns at once and the reader sits in wait() on the tensor's event."""
     from ray_b200.channel import RayChannelError
 
-    a = actors(2)
+    a = actors(2, host_sync=host_sync)
     reader = a.comms[1]
     result = {}
 
@@ -234,7 +237,10 @@ def test_destroy_from_another_thread_unblocks_recv_and_raises(actors):
         with torch.cuda.device(a.devices[1]), torch.cuda.stream(torch.cuda.Stream(a.devices[1])):
             reader._recv_stream = torch.cuda.current_stream()
             try:
-                reader.recv((16,), torch.float32, 0, _alloc(a.dev(1)))
+                t0 = time.time()
+                t = reader.recv((16,), torch.float32, 0, _alloc(a.dev(1)))
+                result["recv_s"] = time.time() - t0
+                reader.wait(t)
                 result["err"] = None
             except RayChannelError as e:
                 result["err"] = e
@@ -247,11 +253,69 @@ def test_destroy_from_another_thread_unblocks_recv_and_raises(actors):
     t.join(10)
     assert not t.is_alive() and time.time() - t0 < 8
     assert isinstance(result.get("err"), RayChannelError)
+    if not host_sync:
+        assert result["recv_s"] < 0.2, "recv() must not block the host in event mode"
     reader.destroy()  # idempotent
     with pytest.raises(RayChannelError):
         reader.send(torch.ones(1, device=a.dev(1)), 0)
     with pytest.raises(RayChannelError):
         reader.allreduce(torch.ones(1, device=a.dev(1)), torch.ones(1, device=a.dev(1)), 0)
+
+
+def test_overlap_recv_does_not_block_the_host_and_is_event_guarded(actors):
+    """overlap_gpu_communication (test_torch_tensor_dag.py overlap cases, dag_operation_future.py:
+    101-133): recv is enqueued on the receive stream and returns immediately -- the host goes on
+    to launch compute -- and the returned tensor carries the event a consumer stream waits on."""
+    a = actors(2, use_communication_streams=True)
+    numel = 1 << 20
+    x = torch.randn(numel, generator=torch.Generator().manual_seed(5))
+
+    def f(r, c):
+        if r == 0:
+            time.sleep(0.4)  # the receiver posts its recv long before the data exists
+            c.send(x.to(a.dev(0)), 1)
+            c._send_stream.synchronize()
+            return None
+        t0 = time.time()
+        got = c.recv((numel,), torch.float32, 0, _alloc(a.dev(1)))
+        dt = time.time() - t0
+        busy = torch.ones(1 << 20, device=a.dev(1))
+        for _ in range(10):  # host keeps launching compute while the recv kernel waits for its peer
+            busy = busy * 1.0001
+        launched_after = time.time() - t0
+        assert got._b200_ready is not None
+        y = got * 2  # current stream already waits on the event: safe without a host sync
+        torch.cuda.current_stream().synchronize()
+        return dt, launched_after, y.cpu()
+
+    dt, launched_after, y = a.run(f)[1]
+    assert dt < 0.2 and launched_after < 0.3, (dt, launched_after)
+    assert torch.equal(y, x * 2)
+
+
+def test_multi_reader_channel_uses_one_broadcast(actors):
+    """A channel that spans the whole group and has several readers moves its payload with ONE
+    broadcast collective instead of a send per reader (the reference's TODO at
+    torch_tensor_accelerator_channel.py:587-590)."""
+    from ray_b200.channel import TorchTensorAcceleratorChannel
+
+    world = 3
+    a = actors(world)
+    chans = [TorchTensorAcceleratorChannel(a.comms[r], 0, [1, 2]) for r in range(world)]
+    assert all(ch._use_broadcast for ch in chans)
+    msg = [torch.randn(1000, 7), torch.arange(33, dtype=torch.int32)]
+
+    def f(r, c):
+        if r == 0:
+            before = c.comm.launch_count
+            chans[0].write([t.to(a.dev(0)) for t in msg])
+            return c.comm.launch_count - before
+        return [t.cpu() for t in chans[r].read()]
+
+    out = a.run(f)
+    assert out[0] == 2 + 2, "2 header sends + ONE broadcast per tensor"
+    for r in (1, 2):
+        assert all(torch.equal(g, m) for g, m in zip(out[r], msg))
 
 
 @pytest.mark.parametrize("world", [2, 3])
