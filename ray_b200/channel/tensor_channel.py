@@ -103,6 +103,10 @@ class TorchTensorAcceleratorChannel:
         world = communicator.get_world_size()
         self._use_broadcast = (len(self._reader_ranks) > 1 and hasattr(communicator, "broadcast") and
                                set(self._reader_ranks) | {writer_rank} == set(range(world)))
+        # pinned allocations synchronise the device implicitly: do it now, not in the middle of a
+        # write()/read() while a peer's kernel may be waiting for ours
+        if me is not None and not static_shape and torch.cuda.is_available():
+            self._headers = _PinnedHeaderRing()
 
     def _raw(self):
         comm = getattr(self._comm, "comm", None)  # the native endpoint (B200Comm) of a B200Communicator

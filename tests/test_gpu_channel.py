@@ -40,6 +40,20 @@ class Actors:
                                  comm_kwargs.get("use_communication_streams", False), store, self.devices[r],
                                  timeout_ms=15000, staging_bytes=8 << 20, inbox_bytes=2 << 20)
             self.comms.append(c)
+        # One persistent stream per actor, with a warmed-up caching-allocator pool.  When actors share
+        # a GPU (fewer devices than ranks) this is a correctness matter for the HARNESS, not for the
+        # library: CUDA forbids two kernels from running concurrently if a device (or pinned)
+        # allocation is issued between their launches (implicit synchronisation), so a cudaMalloc
+        # by one actor between another actor's launch and its own would serialise two kernels that
+        # wait for each other.  Allocations served from torch's cache issue no CUDA call.  (In
+        # production every rank owns its GPU and no co-dependent kernels share a device.)
+        self.streams = [torch.cuda.Stream(self.devices[r]) for r in range(n)]
+        for r in range(n):
+            with torch.cuda.device(self.devices[r]), torch.cuda.stream(self.streams[r]):
+                warm = [torch.empty(1 << 19, dtype=torch.uint8, device=self.dev(r)) for _ in range(3)]
+                warm += [torch.empty(24 << 20, dtype=torch.uint8, device=self.dev(r))]
+                del warm
+        torch.cuda.synchronize()
         self.run(lambda r, c: c.initialize(r))
         if self.shared:
             for c in self.comms:
@@ -51,7 +65,7 @@ class Actors:
         def body(r):
             try:
                 torch.cuda.default_stream(self.devices[r]).synchronize()
-                with torch.cuda.device(self.devices[r]), torch.cuda.stream(torch.cuda.Stream(self.devices[r])):
+                with torch.cuda.device(self.devices[r]), torch.cuda.stream(self.streams[r]):
                     self.comms[r]._cuda_stream = self.comms[r]._cuda_stream or torch.cuda.current_stream()
                     out[r] = fn(r, self.comms[r])
                     torch.cuda.current_stream().synchronize()
