@@ -2,6 +2,7 @@
 // broadcast (K4) and the flag-only barrier (K7).  These kernels move bytes; they do
 // not depend on the element type.
 #include "kernel_utils.cuh"
+#include "pipe.h"
 
 namespace b200 {
 
@@ -133,6 +134,28 @@ extern "C" int b200_allgather(b200_comm_t c, const void *in, void *const *outs, 
   if (c->world == 1) {
     if (outs[0] != in) B200_CHECK_CUDA(cudaMemcpyAsync(outs[0], in, total, cudaMemcpyDeviceToDevice, stream));
     return B200_OK;
+  }
+  // Large aligned operands: the pull kernel (TMA copy-in + bulk loads of the peers' slots straight
+  // into the caller's output tensors, allreduce_pipe.cu).  B200_PARAM_AG_PULL_MIN_BYTES = per-rank
+  // size from which it is used (default 1 MiB; 0 = never).
+  {
+    const long long pm = c->params[B200_PARAM_AG_PULL_MIN_BYTES];
+    const size_t pull_min = pm >= 0 ? size_t(pm) : (size_t(1) << 20);
+    bool aligned = is_aligned16(in) && (total & 15) == 0 && pm != 0 && pipe_max_bytes(c, 0) > 0;
+    for (int p = 0; p < c->world; ++p) aligned = aligned && is_aligned16(outs[p]);
+    if (aligned && total >= pull_min) {
+      const size_t cap = pipe_max_bytes(c, 0) / (size_t(1) << 20) * (size_t(1) << 20);
+      const size_t step = cap ? cap : c->staging_bytes;
+      for (size_t done = 0; done < total;) {
+        const size_t nbytes = (total - done) < step ? (total - done) : step;
+        char *o[kMaxRanks] = {};
+        for (int p = 0; p < c->world; ++p) o[p] = static_cast<char *>(outs[p]) + done;
+        rc = launch_allgather_pull(c, static_cast<const char *>(in) + done, o, nbytes, stream);
+        if (rc) return rc;
+        done += nbytes;
+      }
+      return B200_OK;
+    }
   }
   for (size_t done = 0; done < total;) {
     const size_t nbytes = (total - done) < c->staging_bytes ? (total - done) : c->staging_bytes;

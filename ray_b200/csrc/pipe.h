@@ -19,6 +19,8 @@ size_t pipe_max_bytes(const b200_comm *c, int variant);
 int launch_allreduce_pipe_dyn(b200_comm *c, const char *in, char *out, size_t nbytes, int dtype, int op,
                               int variant, cudaStream_t stream);
 
+// pull all-gather (copy-in | bulk-pull from every peer's slot); same operand requirements
+int launch_allgather_pull(b200_comm *c, const char *in, char *const *outs, size_t nbytes, cudaStream_t stream);
 // cudaFuncAttributeMaxDynamicSharedMemorySize = bulk-copy ring, once per (device, kernel)
 int set_dyn_smem(int device, const void *fn);
 

@@ -89,6 +89,28 @@ def sendrecv(g, args):
     set_all(g, N.PARAM_BULK_CFG, -1)
 
 
+def allgather(g, args):
+    n = g.world_size
+    for total in ([16 * MiB, 64 * MiB, 256 * MiB, 1024 * MiB]):
+        per = total // n // 4
+        xs = [torch.ones(per, device=g.device(r)) for r in range(n)]
+        outs = [torch.empty(per * n, device=g.device(r)) for r in range(n)]
+        iters = 20 if total <= 64 * MiB else 6
+        call = lambda c, r: c.allgather_into(outs[r], xs[r])  # noqa: E731
+        configs = [("staged (r01)", 0, -1, -1)] + [(f"pull copy={cp} pull={pl}", -1, cp, pl) for cp, pl in
+                                                   ((8, 16), (16, 16), (16, 32), (16, 48), (32, 32), (8, 32))]
+        for label, mn, cp, pl in configs:
+            set_all(g, N.PARAM_AG_PULL_MIN_BYTES, mn)
+            set_all(g, N.PARAM_PIPE_COPY_CTAS, cp)
+            set_all(g, N.PARAM_PIPE_RED_CTAS, pl)
+            us = time_graphs(g, call, iters)
+            print(f"allgather n={n} total {total >> 20:5d} MiB {label:24s} {us:9.1f} us  busbw={per * 4 * n / us / 1e3 * (n - 1) / n:7.1f} GB/s",
+                  flush=True)
+        del xs, outs
+    for p in (N.PARAM_AG_PULL_MIN_BYTES, N.PARAM_PIPE_COPY_CTAS, N.PARAM_PIPE_RED_CTAS):
+        set_all(g, p, -1)
+
+
 def gradlocal(g, args):
     # ResNet-50 DDP buckets (fp32 elements): 7.82, 30.04, 25.04, 25.32, 9.27 MB
     for mb in (7.82, 9.27, 25.04, 30.04, 60.0, 240.0):
@@ -127,7 +149,7 @@ def main():
     g = LocalGroup(args.world, timeout_ms=20000, staging_bytes=256 << 20, inbox_bytes=32 << 20)
     print(f"# world={args.world} devices={g.devices} shared={g.shared_gpu} multicast={g.has_multicast}", flush=True)
     for what in args.what.split(","):
-        {"allreduce": allreduce, "sendrecv": sendrecv, "gradlocal": gradlocal}[what](g, args)
+        {"allreduce": allreduce, "sendrecv": sendrecv, "gradlocal": gradlocal, "allgather": allgather}[what](g, args)
     g.destroy()
 
 

@@ -249,3 +249,39 @@ def test_bulk_copy_send_recv_is_byte_exact(native_lib, world):
         for _ in range(3):
             g.run(pingpong)
             assert torch.equal(z.cpu(), x.cpu())
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_pull_allgather_is_byte_exact(pipe_groups, world):
+    """all-gather through the pull kernel (TMA copy-in + bulk loads of every peer's slot straight
+    into the caller's output tensors): sizes around the tile / chunk boundaries, separately
+    allocated outputs and the Compiled-Graph concatenated layout, and the misaligned fallback."""
+    from ray_b200 import _native as N
+
+    g = pipe_groups(world)
+    for nbytes in (MiB, MiB + 16, 2 * MiB - 16, 3 * MiB + 16 * 1001):
+        host = [torch.randint(0, 255, (nbytes,), dtype=torch.uint8, generator=torch.Generator().manual_seed(nbytes % 1000 + r))
+                for r in range(world)]
+        xs = [h.to(g.device(r)) for r, h in enumerate(host)]
+        outs = [[torch.zeros(nbytes, dtype=torch.uint8, device=g.device(r)) for _ in range(world)] for r in range(world)]
+        before = g.comms[0].launch_count
+        g.run(lambda c, r: c.allgather(outs[r], xs[r]))
+        assert g.comms[0].launch_count == before + 1
+        for r in range(world):
+            for p in range(world):
+                assert torch.equal(outs[r][p].cpu(), host[p]), (world, nbytes, r, p)
+        cat = [torch.zeros(world * nbytes, dtype=torch.uint8, device=g.device(r)) for r in range(world)]
+        g.run(lambda c, r: c.allgather_into(cat[r], xs[r]))
+        want = torch.cat(host)
+        for r in range(world):
+            assert torch.equal(cat[r].cpu(), want), (world, nbytes, r)
+    # misaligned input: staged kernel, same bytes
+    nbytes = 2 * MiB
+    host = [torch.randint(0, 255, (nbytes + 1,), dtype=torch.uint8, generator=torch.Generator().manual_seed(9 + r))
+            for r in range(world)]
+    xs = [h.to(g.device(r)) for r, h in enumerate(host)]
+    outs = [[torch.zeros(nbytes, dtype=torch.uint8, device=g.device(r)) for _ in range(world)] for r in range(world)]
+    g.run(lambda c, r: c.allgather(outs[r], xs[r][1:]))
+    for r in range(world):
+        for p in range(world):
+            assert torch.equal(outs[r][p].cpu(), host[p][1:])
