@@ -883,7 +883,8 @@ int launch_allgather_pull(b200_comm *c, const char *in, char *const *outs, size_
   const long long pc = c->params[B200_PARAM_PIPE_COPY_CTAS];
   const long long pr = c->params[B200_PARAM_PIPE_RED_CTAS];
   int G = pc > 0 ? int(pc) : 16;
-  int Gp = pr > 0 ? int(pr) : 32;
+  // pull CTAs also move the rank's own tensor (in -> out): half of all bytes at 2 ranks, 1/8 at 8
+  int Gp = pr > 0 ? int(pr) : (c->world == 2 ? 64 : (c->world <= 4 ? 48 : 32));
   int cap = c->forced_blocks > 0 ? c->forced_blocks : c->sm_count;
   if (G + Gp > cap) {
     while (G > 1 && G + 1 > cap / 2) G /= 2;
