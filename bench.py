@@ -490,10 +490,10 @@ def parity_check(pg, rank, world, device):
                 ok = torch.equal(got, ref)
                 rel = 0.0
             else:
-                ref = host.float()
-                dist.all_reduce(ref)
                 sabs = host.float().abs()
                 dist.all_reduce(sabs)
+                ref = host.float().clone()  # .float() of an fp32 tensor is the tensor itself
+                dist.all_reduce(ref)
                 err = (got.float() - (ref if dtype == torch.float32 else ref.to(dtype).float())).abs()
                 rel = float((err / sabs.clamp_min(1e-30)).max())
                 ok = bool((err <= tol * sabs + 1e-30).all())
@@ -507,10 +507,10 @@ def parity_check(pg, rank, world, device):
     comm.grad_allreduce(gbuf, 1.0 / world, torch.bfloat16)
     torch.cuda.synchronize()
     wire = (host * (1.0 / world)).to(torch.bfloat16).float()
-    ref = wire.clone()
-    dist.all_reduce(ref)
     sabs = wire.abs()
     dist.all_reduce(sabs)
+    ref = wire.clone()
+    dist.all_reduce(ref)
     err = (gbuf.cpu() - ref.to(torch.bfloat16).float()).abs()
     rel = float((err / sabs.clamp_min(1e-30)).max())
     record("grad_allreduce/bf16wire/25MiB", bool((err <= 2.0 ** -7 * sabs + 1e-30).all()) and replicas_identical(gbuf), rel)
@@ -527,10 +527,10 @@ def parity_check(pg, rank, world, device):
     out = torch.empty(per, device=device)
     comm.reducescatter_from(out, full.to(device))
     torch.cuda.synchronize()
-    ref = full.clone()
-    dist.all_reduce(ref)  # the reference's gloo reducescatter is n all-reduces (torch_gloo_collective_group.py:260-282)
     sabs = full.abs()
     dist.all_reduce(sabs)
+    ref = full.clone()
+    dist.all_reduce(ref)  # the reference's gloo reducescatter is n all-reduces (torch_gloo_collective_group.py:260-282)
     sl = slice(rank * per, (rank + 1) * per)
     err = (out.cpu() - ref[sl]).abs()
     rel = float((err / sabs[sl].clamp_min(1e-30)).max())
