@@ -475,7 +475,7 @@ def parity_check(pg, rank, world, device):
 
     MiB = 1 << 20
     # ---- all-reduce fp32 / bf16 / int32 ------------------------------------------------------
-    for dtype, sizes, tol in ((torch.float32, (1 * MiB, 64 * MiB, 256 * MiB), 1e-6), (torch.bfloat16, (1 * MiB, 64 * MiB), 2.0 ** -7),
+    for dtype, sizes, tol in ((torch.float32, (1 * MiB, 64 * MiB, 256 * MiB), 1e-6), (torch.bfloat16, (1 * MiB, 64 * MiB), 2.0 ** -6),
                               (torch.int32, (1 * MiB, 64 * MiB), 0.0)):
         for nbytes in sizes:
             numel = nbytes // torch.empty((), dtype=dtype).element_size()
@@ -513,7 +513,7 @@ def parity_check(pg, rank, world, device):
     dist.all_reduce(ref)
     err = (gbuf.cpu() - ref.to(torch.bfloat16).float()).abs()
     rel = float((err / sabs.clamp_min(1e-30)).max())
-    record("grad_allreduce/bf16wire/25MiB", bool((err <= 2.0 ** -7 * sabs + 1e-30).all()) and replicas_identical(gbuf), rel)
+    record("grad_allreduce/bf16wire/25MiB", bool((err <= 2.0 ** -6 * sabs + 1e-30).all()) and replicas_identical(gbuf), rel)
     del gbuf
     # ---- all-gather, reduce-scatter, broadcast (64 MiB total / per op) ------------------------
     per = 64 * MiB // 4 // world
@@ -544,7 +544,7 @@ def parity_check(pg, rank, world, device):
     flag = torch.tensor([failed], dtype=torch.int64)
     dist.all_reduce(flag)
     summary = {"cases": cases, "failed": int(flag.item()), "max_rel": max_rel, "multicast": bool(comm.has_multicast),
-               "tolerance": "fp32 1e-6*sum|x_r| vs gloo; bf16 2^-7*sum|x_r| (one rounding of an fp32 sum); int/copies bit exact; "
+               "tolerance": "fp32 1e-6*sum|x_r| vs gloo; bf16 2^-6*sum|x_r| (the NVSwitch rounds partial sums in bf16: up to n-1 roundings of 2^-9); int/copies bit exact; "
                             "replicas bit-identical", "detail": detail}
     if summary["failed"]:
         raise RuntimeError(f"parity check failed: {json.dumps(summary)}")

@@ -231,7 +231,7 @@ typedef enum {
   B200_PARAM_GRAD_LOCAL_UNROLL = 9, /* world 1 gradient kernel: 16-byte wire units per thread (1, 2, 4, 8) */
   B200_PARAM_P2P_BULK_MIN_CHUNK = 10, /* send/recv: chunks from this size on move with the TMA bulk-copy kernel (0 = never; default 32 KiB) */
   B200_PARAM_BULK_CFG = 11,         /* send: bulk-engine (lookahead, completion lag) flavour, tuning experiments only */
-  B200_PARAM_AG_PULL_MIN_BYTES = 12, /* all-gather: per-rank size from which the pull kernel is used (0 = never; default 1 MiB) */
+  B200_PARAM_AG_PULL_MIN_BYTES = 12, /* all-gather: per-rank size from which the pull kernel is used (0 = never; default 4 MiB) */
   B200_PARAM_COUNT = 13
 } b200_param_t;
 int b200_comm_set_param(b200_comm_t comm, int param, long long value);

@@ -308,9 +308,10 @@ static size_t oneshot_limit(const b200_comm *c) {
   if (c->params[B200_PARAM_ONESHOT_MAX_BYTES] >= 0) return size_t(c->params[B200_PARAM_ONESHOT_MAX_BYTES]);
   if (env >= 0) return size_t(env);
   // each rank reads world * nbytes in the one-shot scheme.  Break-even against the two-shot kernel
-  // (profiles/r01 sweeps: 2 ranks ~1 MiB, 8 ranks ~256 KiB); the 0.5 MB PPO gradient vector of
-  // BASELINE configs[3] falls on the one-shot side at 2 and 4 ranks.
-  return (size_t(2) << 20) / size_t(c->world);
+  // (profiles/r01 sweeps: 2 ranks ~1 MiB, 8 ranks ~256 KiB; profiles/r02/bench_n4: 256 KiB one-shot
+  // 16 us, 1 MiB two-shot 24 us); the 0.5 MB PPO gradient vector of BASELINE configs[3] falls on
+  // the one-shot side at 2 and 4 ranks.
+  return (size_t(5) << 19) / size_t(c->world);  // 2.5 MiB / n
 }
 
 }  // namespace b200

@@ -259,7 +259,7 @@ def test_pull_allgather_is_byte_exact(pipe_groups, world):
     from ray_b200 import _native as N
 
     g = pipe_groups(world)
-    for nbytes in (MiB, MiB + 16, 2 * MiB - 16, 3 * MiB + 16 * 1001):
+    for nbytes in (4 * MiB, 4 * MiB + 16, 5 * MiB - 16, 6 * MiB + 16 * 1001):
         host = [torch.randint(0, 255, (nbytes,), dtype=torch.uint8, generator=torch.Generator().manual_seed(nbytes % 1000 + r))
                 for r in range(world)]
         xs = [h.to(g.device(r)) for r, h in enumerate(host)]
@@ -276,7 +276,7 @@ def test_pull_allgather_is_byte_exact(pipe_groups, world):
         for r in range(world):
             assert torch.equal(cat[r].cpu(), want), (world, nbytes, r)
     # misaligned input: staged kernel, same bytes
-    nbytes = 2 * MiB
+    nbytes = 5 * MiB
     host = [torch.randint(0, 255, (nbytes + 1,), dtype=torch.uint8, generator=torch.Generator().manual_seed(9 + r))
             for r in range(world)]
     xs = [h.to(g.device(r)) for r, h in enumerate(host)]
