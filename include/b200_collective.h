@@ -186,6 +186,14 @@ int b200_barrier(b200_comm_t comm, void *stream);
 int b200_send(b200_comm_t comm, const void *buf, size_t nbytes, int peer, void *stream);
 int b200_recv(b200_comm_t comm, void *buf, size_t nbytes, int peer, void *stream);
 
+/* One-sided get (RDT's one-sided transport, experimental/rdt/cuda_ipc_transport.py:57-186, without
+ * its same-GPU restriction): copies [src_heap_offset, +nbytes) of rank `src_rank`'s symmetric heap
+ * into `dst` with a kernel that runs on THIS rank only.  The caller orders it after the owner's
+ * writes (an interprocess event in the RDT transport).  b200_symm_base returns this rank's heap
+ * base and size, so that an address inside it can be turned into the offset a peer passes here. */
+int b200_symm_base(b200_comm_t comm, void **base, size_t *bytes);
+int b200_get(b200_comm_t comm, void *dst, int src_rank, size_t src_heap_offset, size_t nbytes, void *stream);
+
 /* Fused data-parallel gradient synchronisation: for a flat fp32
  * bucket computes grad[i] = sum_r wire(grad_r[i] * scale) in one launch, where
  * wire() is a cast to `wire_dtype` (B200_BF16 / B200_F16 compress the NVLink

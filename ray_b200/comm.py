@@ -309,6 +309,32 @@ class B200Comm:
         if st:
             N.check(st)
 
+    # ------------------------------------------------------------------ one-sided get
+    def heap_range(self):
+        """(base address, bytes) of this rank's symmetric heap."""
+        base, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+        N.check(self._lib.b200_symm_base(self._h, ctypes.byref(base), ctypes.byref(nbytes)))
+        return int(base.value or 0), int(nbytes.value)
+
+    def heap_view(self, offset: int, nbytes: int) -> torch.Tensor:
+        """uint8 tensor over [offset, offset+nbytes) of this rank's heap (no allocation bookkeeping)."""
+        base, size = self.heap_range()
+        if offset < 0 or offset + nbytes > size:
+            raise ValueError("range outside the symmetric heap")
+        holder = SymmetricTensorHolder(base + offset, max(nbytes, 1), self)
+        t = torch.as_tensor(holder, device=torch.device("cuda", self.device))[:nbytes]
+        t._b200_holder = holder  # noqa: SLF001
+        return t
+
+    def get(self, dst: torch.Tensor, src_rank: int, src_heap_offset: int,
+            stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Pull ``dst.nbytes`` bytes from ``src_rank``'s symmetric heap into ``dst``; only this rank
+        runs a kernel."""
+        _check_cuda_contiguous(dst)
+        N.check(self._lib.b200_get(self._h, dst.data_ptr(), int(src_rank), int(src_heap_offset),
+                                   dst.numel() * dst.element_size(),
+                                   stream.cuda_stream if stream is not None else self._stream()))
+
     def grad_allreduce(self, grad: torch.Tensor, scale: float, wire_dtype: torch.dtype = torch.bfloat16) -> None:
         """Fused ``grad = sum_r wire(grad_r * scale)`` on a flat fp32 bucket."""
         _check_cuda_contiguous(grad)

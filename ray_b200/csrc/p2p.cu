@@ -214,6 +214,48 @@ __global__ void __launch_bounds__(kThreads, 1) p2p_bulk_kernel(DevComm c, P2PArg
   if (threadIdx.x == 0) *seq_word = seq0 + uint32_t(stop ? mailbox : nq);
 }
 
+// ---------------------------------------------------------------------------
+// one-sided get: the receiver pulls [src_off, src_off + nbytes) of a PEER's symmetric heap into a
+// local tensor.  No kernel runs on the owner of the data (RDT's one-sided contract,
+// experimental/rdt/cuda_ipc_transport.py:57-186); ordering against the owner's writes is the
+// caller's event.  Aligned transfers use bulk loads over NVLink + bulk stores (segment engine).
+// ---------------------------------------------------------------------------
+struct GetArgs {
+  const char *src;  // peer mapping of the owner's heap + offset
+  char *dst;
+  size_t nbytes;
+  size_t seg_bytes;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) get_bulk_kernel(GetArgs a) {
+  extern __shared__ __align__(128) char dyn_smem[];
+  const BulkRing br = bulk_ring_init(dyn_smem);
+  if (threadIdx.x != 0) return;
+  const size_t nseg = (a.nbytes + a.seg_bytes - 1) / a.seg_bytes;
+  const uint32_t b = blockIdx.x, G = gridDim.x;
+  const uint32_t mine = nseg > b ? uint32_t((nseg - 1 - b) / G + 1) : 0;
+  bulk_copy_segments<BulkPull>(
+      br, mine,
+      [&](uint32_t i) {
+        const size_t lo = (size_t(b) + size_t(i) * G) * a.seg_bytes;
+        const uint32_t len = uint32_t((a.nbytes - lo) < a.seg_bytes ? (a.nbytes - lo) : a.seg_bytes);
+        return BulkSeg{a.src + lo, a.dst + lo, len};
+      },
+      [&](uint32_t, bool) { return 1; }, [&](uint32_t) {});
+}
+
+__global__ void __launch_bounds__(kThreads) get_ldst_kernel(GetArgs a) {
+  const Units un = make_units(a.nbytes);
+  const size_t U = un.total();
+  const bool sal = is_aligned16(a.src), dal = is_aligned16(a.dst);
+  for (size_t u = size_t(blockIdx.x) * kThreads + threadIdx.x; u < U; u += size_t(gridDim.x) * kThreads) {
+    uint4 v;
+    if (sal && u < un.full) v = ld_peer(a.src + (u << 4));
+    else v = load_user_unit(a.src, u, un, false);
+    store_user_unit(a.dst, u, un, dal, v);
+  }
+}
+
 static int p2p_common(b200_comm *c, void *buf, size_t nbytes, int peer, cudaStream_t stream, bool send) {
   int rc = check_usable(c);
   if (rc) return rc;
@@ -265,4 +307,47 @@ extern "C" int b200_send(b200_comm_t c, const void *buf, size_t nbytes, int peer
 
 extern "C" int b200_recv(b200_comm_t c, void *buf, size_t nbytes, int peer, void *stream) {
   return p2p_common(c, buf, nbytes, peer, static_cast<cudaStream_t>(stream), false);
+}
+
+extern "C" int b200_symm_base(b200_comm_t c, void **base, size_t *bytes) {
+  int rc = check_usable(c);
+  if (rc) return rc;
+  if (base) *base = reinterpret_cast<char *>(c->data.va[c->rank]) + 2 * c->staging_bytes;
+  if (bytes) *bytes = c->heap_bytes;
+  return B200_OK;
+}
+
+extern "C" int b200_get(b200_comm_t c, void *dst, int src_rank, size_t src_heap_offset, size_t nbytes, void *stream_) {
+  int rc = check_usable(c);
+  if (rc) return rc;
+  if (src_rank < 0 || src_rank >= c->world) {
+    set_error("source rank %d out of range for world size %d", src_rank, c->world);
+    return B200_ERR_INVALID;
+  }
+  if (src_heap_offset + nbytes > c->heap_bytes) {
+    set_error("[%zu, %zu) is outside the %zu-byte symmetric heap", src_heap_offset, src_heap_offset + nbytes,
+              c->heap_bytes);
+    return B200_ERR_INVALID;
+  }
+  if (nbytes == 0) return B200_OK;
+  if (!dst) {
+    set_error("null tensor pointer");
+    return B200_ERR_INVALID;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200_CHECK_CUDA(cudaSetDevice(c->device));
+  GetArgs a{reinterpret_cast<const char *>(c->data.va[src_rank]) + 2 * c->staging_bytes + src_heap_offset,
+            static_cast<char *>(dst), nbytes, size_t(256) << 10};
+  if (is_aligned16(a.src) && is_aligned16(a.dst) && (nbytes & 15) == 0 && nbytes >= (size_t(256) << 10)) {
+    const size_t nseg = (nbytes + a.seg_bytes - 1) / a.seg_bytes;
+    const int g = int(nseg < 16 ? nseg : 16);
+    if (int rc2 = set_dyn_smem(c->device, reinterpret_cast<const void *>(get_bulk_kernel))) return rc2;
+    get_bulk_kernel<<<g, kThreads, kBulkSmemBytes, stream>>>(a);
+  } else {
+    const size_t U = make_units(nbytes).total();
+    const int g = int((U + kThreads - 1) / kThreads < 32 ? (U + kThreads - 1) / kThreads : 32);
+    get_ldst_kernel<<<g, kThreads, 0, stream>>>(a);
+  }
+  B200_LAUNCH_CHECK(c);
+  return B200_OK;
 }

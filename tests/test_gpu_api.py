@@ -290,3 +290,64 @@ def test_rdt_tensor_transport_over_b200_group(workers):
         tr.garbage_collect("obj-1", meta_t, sent)
     finally:
         B200TensorTransport.group_resolver = None
+
+
+def test_rdt_one_sided_transport_pulls_without_the_sender(workers, monkeypatch):
+    """RDT one-sided ``B200_IPC`` transport.  extract_tensor_transport_metadata
+    publishes (heap offset, event); recv_multiple_tensors pulls with a receiver-side kernel into
+    target_buffers; the sender's communicator launches nothing (cuda_ipc_transport.py:57-186 is the
+    pattern, without its same-GPU restriction)."""
+    import threading
+
+    from ray_b200.rdt import B200IpcTransport, B200IpcTransportMetadata
+
+    monkeypatch.setenv("B200_HEAP_BYTES", str(64 << 20))
+    w = workers(2)
+    w.init("ipc-group")
+    tr = B200IpcTransport()
+    assert tr.tensor_transport_backend() == "B200_IPC" and tr.is_one_sided() and tr.can_abort_transport()
+    B200IpcTransport.group_resolver = staticmethod(lambda src, dst: ("ipc-group", int(src[-1]), int(dst[-1])))
+    B200IpcTransport.publish_resolver = staticmethod(lambda: ("ipc-group", 0))
+    box, ready, done = {}, threading.Event(), threading.Event()
+    payload = [torch.randn(1 << 20), torch.arange(1003, dtype=torch.int32), torch.randn(7, 9).to(torch.float16)]
+    try:
+        meta_c = tr.get_communicator_metadata("actor0", "actor1", "B200_IPC")
+
+        def f(r):
+            comm = w.col.get_group_handle("ipc-group").comm
+            if r == 0:
+                sent = [t.to(w.dev(0)) for t in payload]
+                in_heap = comm.symm_empty((4096,), torch.float32)  # already symmetric: published in place
+                in_heap.copy_(torch.arange(4096, dtype=torch.float32))
+                before = comm.launch_count
+                box["meta"] = tr.extract_tensor_transport_metadata("obj-9", sent + [in_heap])
+                ready.set()
+                done.wait(60)
+                launches = comm.launch_count - before
+                tr.garbage_collect("obj-9", box["meta"], sent)
+                return launches
+            ready.wait(60)
+            meta = box["meta"]
+            assert isinstance(meta, B200IpcTransportMetadata) and meta.src_rank == 0 and len(meta.heap_offsets) == 4
+            targets = [torch.zeros(tuple(s), dtype=d, device=w.dev(1)) for s, d in meta.tensor_meta]
+            got = tr.recv_multiple_tensors("obj-9", meta, meta_c, target_buffers=targets)
+            torch.cuda.current_stream().synchronize()
+            assert all(g.data_ptr() == t.data_ptr() for g, t in zip(got, targets)), "must land in target_buffers"
+            out = [g.cpu() for g in got]
+            again = tr.recv_multiple_tensors("obj-9", meta, meta_c)  # a second consumer allocates its own
+            torch.cuda.current_stream().synchronize()
+            done.set()
+            return out, [a.cpu() for a in again]
+
+        res = w.run(f)
+        assert res[0] == 0, "the sender must not launch a single kernel of the library"
+        for got in res[1]:
+            assert all(torch.equal(g, p) for g, p in zip(got[:3], payload))
+            assert torch.equal(got[3], torch.arange(4096, dtype=torch.float32))
+        with pytest.raises(NotImplementedError):
+            tr.send_multiple_tensors([], None, None)
+        assert tr._staged == {}
+    finally:
+        done.set()
+        B200IpcTransport.group_resolver = None
+        B200IpcTransport.publish_resolver = None

@@ -141,3 +141,21 @@ def test_operand_checks_fire_before_the_gpu_is_touched():
     with pytest.raises(RuntimeError, match="same dtype"):
         _check_same_shape_dtype(a, [torch.zeros(2, 3, dtype=torch.float64)])
     assert col.B200Group.backend() == "B200"
+
+
+def test_rdt_heap_arena_first_fit_and_coalescing():
+    from ray_b200.rdt import _HeapArena
+
+    a = _HeapArena(4096, 1 << 20)
+    x, y, z = a.alloc(1000), a.alloc(70000), a.alloc(1)
+    assert x == 4096 and y == 4096 + 1024 and z % 256 == 0 and len({x, y, z}) == 3
+    a.free(y)
+    assert a.alloc(60000) == y  # first fit reuses the hole
+    a.free(x)
+    a.free(z)
+    a.free(y)
+    assert a._free == [(4096, 1 << 20)]  # everything coalesced back
+    import pytest
+
+    with pytest.raises(MemoryError):
+        a.alloc((1 << 20) + 1)
