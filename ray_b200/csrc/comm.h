@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <array>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -70,6 +71,8 @@ struct b200_comm {
   std::thread server;
   std::atomic<bool> server_stop{false};
   std::vector<std::string> peer_socks;
+  unsigned char token[16] = {};                          // secret of this rank's endpoint
+  std::vector<std::array<unsigned char, 16>> peer_tokens;  // ... and of the peers', from their handles
   bool connected = false;
   uint32_t host_barrier_seq = 0;
 

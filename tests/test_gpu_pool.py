@@ -57,3 +57,47 @@ def test_mem_pool_tensors_are_zero_copy_operands(native_lib):
     with tempfile.TemporaryDirectory() as store_dir, tempfile.TemporaryDirectory() as out_dir:
         mp.spawn(_worker, args=(world, store_dir, out_dir), nprocs=world, join=True)
         assert all(os.path.exists(os.path.join(out_dir, f"ok{r}")) for r in range(world))
+
+
+def test_bootstrap_endpoint_requires_the_token_and_stops_serving_after_connect(native_lib):
+    """the fd-passing endpoint must not hand GPU memory to whoever connects.
+    Before connect: a request without the 128-bit token from the handle blob gets nothing.  After
+    connect: the endpoint is closed."""
+    import ctypes
+    import socket
+    import struct
+    import time
+
+    from ray_b200 import _native as N
+    from ray_b200.testing import LocalGroup
+
+    lib = native_lib
+    h = ctypes.c_void_p()
+    cfg = N.B200Config(2 << 20, 0, 2 << 20, 0, 1000)
+    N.check(lib.b200_comm_create(2, 0, 0, ctypes.byref(cfg), ctypes.byref(h)))
+    try:
+        blob = ctypes.create_string_buffer(N.HANDLE_BYTES)
+        N.check(lib.b200_comm_export_handle(h, blob))
+        raw = blob.raw
+        name = raw[raw.index(b"b200coll-"):].split(b"\0")[0]
+        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        s.settimeout(3)
+        s.connect(b"\0" + name)
+        s.sendall(struct.pack("<IIIi16s", 0xB200C011, 1, 0, 0, b"\0" * 16))  # GET_FD(data), wrong token
+        msg, anc, _, _ = s.recvmsg(4, socket.CMSG_SPACE(4))
+        assert msg == b"" and not anc, "a request without the token must be dropped"
+        s.close()
+    finally:
+        lib.b200_comm_destroy(h)
+    with LocalGroup(2, staging_bytes=2 << 20, inbox_bytes=2 << 20) as g:
+        blob = ctypes.create_string_buffer(N.HANDLE_BYTES)
+        N.check(lib.b200_comm_export_handle(g.comms[0]._h, blob))
+        name = blob.raw[blob.raw.index(b"b200coll-"):].split(b"\0")[0]
+        time.sleep(0.3)  # the server thread leaves its loop within one 100 ms poll
+        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        with pytest.raises((ConnectionRefusedError, FileNotFoundError)):
+            s.connect(b"\0" + name)
+        s.close()
+        x = [torch.ones(10, device=g.device(r)) for r in range(2)]
+        g.run(lambda c, r: c.allreduce(x[r]))  # the group works without its endpoint
+        assert all(torch.all(t == 2) for t in x)
