@@ -254,6 +254,7 @@ class B200IpcTransport(B200TensorTransport):
     def __init__(self):
         self._arenas = {}
         self._staged = {}  # obj_id -> list of (group, offset)
+        self._ipc_events = {}
 
     def tensor_transport_backend(self) -> str:
         return "B200_IPC"
@@ -315,13 +316,17 @@ class B200IpcTransport(B200TensorTransport):
             meta.nbytes.append(int(nbytes))
         self._staged[obj_id] = staged
         # the receiver's pull must come after everything the sender enqueued so far
-        event = torch.cuda.Event(interprocess=True)
-        torch.cuda.current_stream(device).record_event(event)
-        B200IpcTransport._same_process_events[(meta.src_pid, obj_id)] = event
+        stream = torch.cuda.current_stream(device)
+        plain = torch.cuda.Event()  # consumers in this process (thread actors) wait on this one:
+        plain.record(stream)        # an IPC handle cannot be opened by the process that created it
+        B200IpcTransport._same_process_events[(meta.src_pid, obj_id)] = plain
         try:
-            meta.event_ipc_handle = event.ipc_handle()
+            shared = torch.cuda.Event(interprocess=True)
+            shared.record(stream)
+            meta.event_ipc_handle = shared.ipc_handle()
+            self._ipc_events[obj_id] = shared  # keep it alive until garbage_collect
         except Exception:  # pragma: no cover - e.g. a driver that cannot export events
-            event.synchronize()
+            plain.synchronize()
         return meta
 
     def get_communicator_metadata(self, src_actor, dst_actor, backend: Optional[str] = None) -> B200CommunicatorMetadata:
@@ -362,3 +367,4 @@ class B200IpcTransport(B200TensorTransport):
             if arena is not None:
                 arena.free(off)
         B200IpcTransport._same_process_events.pop((os.getpid(), obj_id), None)
+        self._ipc_events.pop(obj_id, None)
