@@ -260,11 +260,11 @@ def run_gpu(args):
 
     def ncu_traffic():
         """dram__bytes_read.sum + dram__bytes_write.sum per launch of grad_local_kernel from the
-        committed `ncu --set full` capture (profiles/r01/grad_local_kernel_ncu_full.csv)."""
+        committed `ncu --set full` capture (profiles/r02/grad_local_kernel_ncu_full.csv)."""
         try:
             import csv
 
-            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01", "grad_local_kernel_ncu_full.csv"))))
+            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r02", "grad_local_kernel_ncu_full.csv"))))
             hdr, units, data = rows[0], rows[1], rows[2:]
             ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

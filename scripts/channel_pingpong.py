@@ -2,8 +2,9 @@
 
 Follows the reference microbenchmark's raw-communicator loop (``exec_nccl_gpu`` in
 release/microbenchmark/experimental/compiled_graph_gpu_microbenchmark.py:380-408): rank 0 sends a
-fp16 tensor, rank 1 receives it and sends it back; both synchronise every iteration (the
-reference's ``_NcclGroup`` synchronises after each recv).  Reports the round-trip time per size
+fp16 tensor, rank 1 receives it and sends it back.  The reference's ``_NcclGroup`` synchronises the
+host after each recv; the B200 communicator hands tensors over by CUDA event instead (rank 0
+waits once per round trip, rank 1 never).  Reports the round-trip time per size
 for the B200 communicator and, as comparator, for torch.distributed NCCL send/recv.
 
     python scripts/channel_pingpong.py            # spawns 2 processes on GPUs 0 and 1
@@ -48,20 +49,20 @@ def worker(rank, store_dir, out_path):
         for name in ("b200_raw", "b200_channel", "nccl"):
             def one():
                 if name == "b200_raw":
+                    # event mode (default): no host sync per op.  Rank 1 forwards the tensor it
+                    # received on the same stream, so its host never waits; rank 0 waits once per
+                    # round trip (that wait IS the round-trip time being measured).
                     if rank == 0:
                         comm.send(x, 1)
-                        comm.recv((numel,), torch.float16, 1, alloc)
+                        comm.wait(comm.recv((numel,), torch.float16, 1, alloc))
                     else:
-                        y = comm.recv((numel,), torch.float16, 0, alloc)
-                        comm.send(y, 0)
-                        torch.cuda.current_stream().synchronize()
+                        comm.send(comm.recv((numel,), torch.float16, 0, alloc), 0)
                 elif name == "b200_channel":
                     if rank == 0:
                         fwd.write(x)
-                        back.read()
+                        comm.wait(back.read())
                     else:
                         back.write(fwd.read())
-                        torch.cuda.current_stream().synchronize()
                 else:
                     if rank == 0:
                         dist.send(x, 1)

@@ -39,4 +39,13 @@ with open(f"{dst}/nvlink_kernels_n{W}.csv", "w") as f:
                     round(m["nvlrx__bytes.sum"] / 1e6, 2) if "nvlrx__bytes.sum" in m else None,
                     round(m["nvltx__bytes.sum"] / 1e6, 2) if "nvltx__bytes.sum" in m else None,
                     round((rd + wr) / t, 1) if t and rd is not None else None])
+with open(f"{dst}/ncu_app_range_n{W}.csv", "w") as f:  # the raw per-case ncu rows
+    w = csv.writer(f)
+    w.writerow(["case", "device", "metric", "unit", "value"])
+    for name_file in sorted(glob.glob(f"{src}/ncu_n{W}/case_*.name")):
+        path = name_file[:-5] + ".csv"
+        if os.path.exists(path):
+            for r in csv.DictReader([l for l in open(path) if not l.startswith("==")]):
+                if r.get("Metric Name"):
+                    w.writerow([open(name_file).read().strip(), r["Device"], r["Metric Name"], r["Metric Unit"], r["Metric Value"]])
 print(open(f"{dst}/nvlink_kernels_n{W}.csv").read())
