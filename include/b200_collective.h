@@ -240,7 +240,8 @@ typedef enum {
   B200_PARAM_P2P_BULK_MIN_CHUNK = 10, /* send/recv: chunks from this size on move with the TMA bulk-copy kernel (0 = never; default 32 KiB) */
   B200_PARAM_BULK_CFG = 11,         /* send: bulk-engine (lookahead, completion lag) flavour, tuning experiments only */
   B200_PARAM_AG_PULL_MIN_BYTES = 12, /* all-gather: per-rank size from which the pull kernel is used (0 = never; default 4 MiB) */
-  B200_PARAM_COUNT = 13
+  B200_PARAM_PIPE_RING = 13,        /* n >= 3 pipeline: 0 = split messages larger than the staging slot into several launches; default: one launch, the slot is a ring of chunks */
+  B200_PARAM_COUNT = 14
 } b200_param_t;
 int b200_comm_set_param(b200_comm_t comm, int param, long long value);
 

@@ -40,6 +40,8 @@ struct PipeArgs {
   size_t staging_bytes;
   size_t chunk_bytes;    // C: multiple of copy_ctas * kBulkTile
   int copy_ctas;         // CTAs per copy role (power of two)
+  uint32_t ring_chunks;  // 0: chunk k lives at slot offset k*C (message fits the slot);
+                         // R > 0: chunk k lives at (k % R)*C -- the slot is a ring of R chunks
 };
 
 struct PipeGeom {
@@ -47,6 +49,7 @@ struct PipeGeom {
   uint32_t K;      // chunks
   uint32_t G;      // copy CTAs per role
   uint32_t share;  // bytes of a full chunk each copy CTA moves: C / G (a multiple of kBulkTile)
+  uint32_t R;      // ring length in chunks (0 = no ring)
 };
 __device__ __forceinline__ PipeGeom make_geom(const PipeArgs &a) {
   PipeGeom g;
@@ -55,6 +58,7 @@ __device__ __forceinline__ PipeGeom make_geom(const PipeArgs &a) {
   g.K = uint32_t((g.S + g.C - 1) / g.C);
   g.G = uint32_t(a.copy_ctas);
   g.share = uint32_t(g.C / g.G);
+  g.R = a.ring_chunks;
   return g;
 }
 __device__ __forceinline__ size_t chunk_len(const PipeGeom &g, uint32_t k) {
@@ -64,6 +68,13 @@ __device__ __forceinline__ size_t chunk_len(const PipeGeom &g, uint32_t k) {
 // Copy CTA j moves bytes [j*share, (j+1)*share) of every chunk (clipped by the message end).
 __device__ __forceinline__ size_t share_off(const PipeGeom &g, uint32_t j, uint32_t k) {
   return size_t(k) * g.C + size_t(j) * g.share;
+}
+// Where chunk k sits in the staging slot.  With a ring the slot holds R chunks and chunk k reuses
+// the place of chunk k - R, so ONE launch handles a message of any size with R*C bytes of staging:
+// the copy-in of chunk k (share j) waits until the copy-out of chunk k - R (share j) is done, which
+// in turn implies every rank's reducers are done with chunk k - R (they published it).
+__device__ __forceinline__ size_t slot_chunk_off(const PipeGeom &g, uint32_t k) {
+  return size_t(g.R ? k % g.R : k) * g.C;
 }
 __device__ __forceinline__ uint32_t share_len(const PipeGeom &g, uint32_t j, uint32_t k) {
   const size_t len = chunk_len(g, k), lo = size_t(j) * g.share;
@@ -217,13 +228,20 @@ __device__ __forceinline__ void role_copy_in(const DevComm &c, const PipeArgs &a
   const uint32_t my_chunks = chunks_of_cta(g, j);
   if (threadIdx.x == 0) {
     char *slot = c.data[c.rank] + off;
+    const uint32_t tag = (ep >> 2) << 10;  // launch << 10
     const bool ok = bulk_copy_segments<BulkLocal>(
         ring, my_chunks,
         [&](uint32_t k) {
-          const size_t o = share_off(g, j, k);
-          return BulkSeg{a.in + o, slot + o, share_len(g, j, k)};
+          return BulkSeg{a.in + share_off(g, j, k), slot + slot_chunk_off(g, k) + size_t(j) * g.share, share_len(g, j, k)};
         },
-        [&](uint32_t, bool) { return 1; }, [&](uint32_t k) { mailbox_post(&mb, k + 1); });
+        [&](uint32_t k, bool block) {
+          if (g.R == 0 || k < g.R) return 1;
+          const uint32_t *prog = &c.st->pipe_out_progress[j];
+          const uint32_t need = tag + (k - g.R + 1);
+          if (block) return wait_flag_ge(c, prog, need) ? 1 : -1;
+          return int32_t(ld_acquire_sys(prog) - need) >= 0 ? 1 : 0;
+        },
+        [&](uint32_t k) { mailbox_post(&mb, k + 1); });
     if (!ok) mb.stop = 1;
   } else if (threadIdx.x == 32) {
     copy_flag_thread(c, g, &mb, my_chunks, ep + 1);
@@ -346,7 +364,7 @@ __global__ void __launch_bounds__(kThreads + 32, 1) allreduce_pipe_kernel(DevCom
           }
           if (!alive) break;
         }
-        const size_t cbase = off + size_t(k) * g.C;
+        const size_t cbase = off + slot_chunk_off(g, k);
         const size_t hi = iter.hi;
         const size_t u0 = iter.lo + iter.it * kItemUnits + threadIdx.x;
         if (NVLS) {
@@ -421,13 +439,18 @@ __global__ void __launch_bounds__(kThreads + 32, 1) allreduce_pipe_kernel(DevCom
     const uint32_t my_chunks = chunks_of_cta(g, j);
     if (threadIdx.x == 0) {
       const char *slot = c.data[r] + off;
+      const uint32_t tag = launch << 10;
       bulk_copy_segments<BulkLocal>(
           ring, my_chunks,
           [&](uint32_t k) {
-            const size_t o = share_off(g, j, k);
-            return BulkSeg{slot + o, a.out + o, share_len(g, j, k)};
+            return BulkSeg{slot + slot_chunk_off(g, k) + size_t(j) * g.share, a.out + share_off(g, j, k), share_len(g, j, k)};
           },
-          [&](uint32_t k, bool block) { return scout_gate(&sc, k, block); }, [&](uint32_t) {});
+          [&](uint32_t k, bool block) { return scout_gate(&sc, k, block); },
+          [&](uint32_t k) {
+            // chunk k has left the slot (its bulk loads landed long ago, its stores completed):
+            // the copy-in CTA with the same share may reuse the ring position
+            if (g.R) *reinterpret_cast<volatile uint32_t *>(&c.st->pipe_out_progress[j]) = tag + k + 1;
+          });
     } else if (threadIdx.x == 32) {
       scout_thread(c, kSigPipe1, ep + 2, my_chunks, &sc);
     }
@@ -800,11 +823,18 @@ size_t pipe_chunk_bytes(const b200_comm *c) {
   return C < fit ? C : fit;                                 // 0: slot too small for the pipeline
 }
 
+// chunk ring of the n >= 3 pipeline (B200_PARAM_PIPE_RING: 0 disables it)
+static bool pipe_ring_enabled(const b200_comm *c, int variant) {
+  if (variant != PIPE_NVLS && variant != PIPE_PEER) return false;  // pull kernels: the READER is a peer
+  if (c->params[B200_PARAM_PIPE_RING] == 0) return false;
+  const size_t C = pipe_chunk_bytes(c);
+  return C && c->staging_bytes / C >= 4;
+}
+
 size_t pipe_max_bytes(const b200_comm *c, int variant) {
-  (void)variant;
   const size_t C = pipe_chunk_bytes(c);
   if (C == 0) return 0;
-  size_t cap = c->staging_bytes;
+  size_t cap = pipe_ring_enabled(c, variant) ? ~size_t(0) : c->staging_bytes;
   const size_t by_chunks = size_t(kMaxPipeChunks) * C;
   cap = cap < by_chunks ? cap : by_chunks;
   return cap / C * C;  // whole chunks, so a split message continues on a chunk boundary
@@ -813,7 +843,9 @@ size_t pipe_max_bytes(const b200_comm *c, int variant) {
 template <typename T, int OP>
 int launch_allreduce_pipe(b200_comm *c, const char *in, char *out, size_t nbytes, int variant,
                           cudaStream_t stream) {
-  PipeArgs a{in, out, nbytes, c->staging_bytes, pipe_chunk_bytes(c), 0};
+  PipeArgs a{in, out, nbytes, c->staging_bytes, pipe_chunk_bytes(c), 0, 0};
+  if (pipe_ring_enabled(c, variant) && nbytes > c->staging_bytes / a.chunk_bytes * a.chunk_bytes)
+    a.ring_chunks = uint32_t(c->staging_bytes / a.chunk_bytes);
   const long long pc = c->params[B200_PARAM_PIPE_COPY_CTAS];
   const long long pr = c->params[B200_PARAM_PIPE_RED_CTAS];
   int G = pc > 0 ? int(pc) : (variant == PIPE_PULL ? 32 : 16);
@@ -878,7 +910,7 @@ int launch_allreduce_pipe_dyn(b200_comm *c, const char *in, char *out, size_t nb
 
 // in / outs[p] 16-byte aligned, nbytes a multiple of 16 and <= pipe_max_bytes()
 int launch_allgather_pull(b200_comm *c, const char *in, char *const *outs, size_t nbytes, cudaStream_t stream) {
-  PipeArgs a{in, nullptr, nbytes, c->staging_bytes, pipe_chunk_bytes(c), 0};
+  PipeArgs a{in, nullptr, nbytes, c->staging_bytes, pipe_chunk_bytes(c), 0, 0};
   if (c->params[B200_PARAM_PIPE_CHUNK_BYTES] <= 0) a.chunk_bytes = round_up(size_t(1) << 20, size_t(32) * kBulkTile);
   const long long pc = c->params[B200_PARAM_PIPE_COPY_CTAS];
   const long long pr = c->params[B200_PARAM_PIPE_RED_CTAS];

@@ -78,7 +78,7 @@ struct b200_comm {
 
   std::atomic<uint64_t> launches{0};
   int forced_blocks = 0;
-  long long params[B200_PARAM_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+  long long params[B200_PARAM_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
   int sm_count = 148;
   std::atomic<bool> aborted{false};
   std::mutex mu;

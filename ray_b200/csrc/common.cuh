@@ -57,6 +57,7 @@ struct LocalState {
   uint32_t send_seq[kMaxRanks][kP2PRings];  // next chunk sequence to peer, per ring
   uint32_t recv_seq[kMaxRanks][kP2PRings];  // next chunk sequence from peer, per ring
   uint32_t pipe_cnt[2][kMaxPipeChunks];     // per-chunk arrival counters of the pipelined kernels
+  uint32_t pipe_out_progress[32];           // chunk ring: (launch << 10 | chunks copied out) per copy-out CTA
 };
 
 // Passed by value to every kernel.

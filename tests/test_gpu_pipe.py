@@ -285,3 +285,34 @@ def test_pull_allgather_is_byte_exact(pipe_groups, world):
     for r in range(world):
         for p in range(world):
             assert torch.equal(outs[r][p].cpu(), host[p][1:])
+
+
+@pytest.mark.parametrize("world", [3, 4])
+def test_chunk_ring_handles_messages_larger_than_the_staging_slot_in_one_launch(pipe_groups, world):
+    """n >= 3 pipeline with the slot used as a ring of chunks: a message several times the slot
+    size goes through ONE launch (copy-in of chunk k waits for the copy-out of chunk k - R);
+    B200_PARAM_PIPE_RING=0 splits it into several launches and must give the same bits."""
+    from ray_b200 import _native as N
+
+    g = pipe_groups(world)  # 40 MiB staging slot
+    numel = (97 * MiB + 16 * 3) // 4
+    host = [(torch.arange(numel, dtype=torch.float32) % 1021) * (r + 1) - 3 * r for r in range(world)]
+    want = sum(host)
+    try:
+        for chunk in (1 * MiB, 4 * MiB):
+            for ring in (-1, 0):
+                for c in g.comms:
+                    c.set_param(N.PARAM_PIPE_CHUNK_BYTES, chunk)
+                    c.set_param(N.PARAM_PIPE_RING, ring)
+                xs = [h.to(g.device(r)) for r, h in enumerate(host)]
+                before = g.comms[0].launch_count
+                g.run(lambda c, r: c.allreduce(xs[r], N.SUM, algo=N.ALGO_PIPE))
+                launches = g.comms[0].launch_count - before
+                assert launches == (1 if ring == -1 else 3), (chunk, ring, launches)
+                for r in range(world):
+                    assert torch.equal(xs[r].cpu(), want), (world, chunk, ring, r)
+                del xs
+    finally:
+        for c in g.comms:
+            c.set_param(N.PARAM_PIPE_CHUNK_BYTES, -1)
+            c.set_param(N.PARAM_PIPE_RING, -1)
