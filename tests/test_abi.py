@@ -73,4 +73,8 @@ def test_sass_contains_blackwell_multicast_and_sys_scope_flags(native_lib):
     text = sass.stdout
     assert "sm_100a" in text
     assert "LDGMC" in text, "multimem.ld_reduce missing from SASS"
+    # north_star: "TMA bulk staging into shared memory": cp.async.bulk -> UBLKCP, mbarrier -> SYNCS
+    assert "UBLKCP" in text and "SYNCS" in text, "bulk-copy engine (cp.async.bulk + mbarrier) missing from SASS"
+    for kernel in ("p2p_bulk_kernel", "allreduce_pull_kernel", "allreduce_pipe_kernel", "allgather_pull_kernel", "get_bulk_kernel"):
+        assert kernel in text, kernel
     assert re.search(r"ST\w*\.E\.\w*STRONG\.SYS|STG\.E\.STRONG\.SYS", text), "system-scope flag stores missing"
