@@ -121,8 +121,23 @@ class B200Comm:
             raise
 
     # ------------------------------------------------------------------ helpers
-    def _stream(self) -> int:
-        return torch.cuda.current_stream(self.device).cuda_stream
+    def _stream(self, stream: Optional[torch.cuda.Stream] = None) -> int:
+        """Raw handle of the stream an op is enqueued on (default: this device's current stream).
+
+        The kernels read the communicator's launch counter at entry and rely on STREAM ORDER for
+        their epoch and slot parity (include/b200_collective.h: "collectives of one communicator
+        must be stream-ordered").  A caller that switches streams between two ops of the same
+        communicator is therefore ordered here on the device: the new stream waits for
+        an event recorded at the tail of the previous one.  Costs nothing while the stream stays
+        the same."""
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        last = getattr(self, "_last_stream", None)
+        if last is not None and last.cuda_stream != st.cuda_stream:
+            ev = torch.cuda.Event()
+            ev.record(last)
+            st.wait_event(ev)
+        self._last_stream = st
+        return st.cuda_stream
 
     @property
     def has_multicast(self) -> bool:

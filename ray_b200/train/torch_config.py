@@ -31,6 +31,9 @@ from .process_group import BACKEND_NAME, register_b200_backend
 
 logger = logging.getLogger(__name__)
 
+#: ranks of one b200 group: the GPUs of one HGX host (B200_MAX_RANKS in include/b200_collective.h)
+MAX_B200_WORLD = 8
+
 #: CUDA tensors -> hand-written kernels; CPU tensors (object collectives) -> gloo
 DEFAULT_GPU_BACKEND = f"cpu:gloo,cuda:{BACKEND_NAME}"
 
@@ -54,6 +57,12 @@ def setup_torch_process_group(backend: str, world_rank: int, world_size: int, in
     level = logging.INFO if world_rank == 0 else logging.DEBUG
     logger.log(level, "Setting up process group for: %s [rank=%d, world_size=%d] using %s", init_method,
                world_rank, world_size, backend)
+    if uses_b200(backend) and world_size > MAX_B200_WORLD:
+        # one NVSwitch domain of one host: beyond that the reference's own default applies
+        # (config.py:189-196 picks nccl for GPU workers)
+        logger.warning("b200 groups span at most %d ranks on one host; %d workers requested -> falling back to "
+                       "the nccl backend", MAX_B200_WORLD, world_size)
+        backend = "nccl"
     if uses_b200(backend):
         register_b200_backend()
     dist.init_process_group(backend=backend, init_method=init_method, rank=world_rank, world_size=world_size,

@@ -159,3 +159,37 @@ def test_rdt_heap_arena_first_fit_and_coalescing():
 
     with pytest.raises(MemoryError):
         a.alloc((1 << 20) + 1)
+
+
+def test_stream_switch_between_collectives_is_ordered_on_the_device(monkeypatch):
+    """two collectives of one communicator issued from different streams must not
+    race on the device-resident launch counter: the second stream waits for the tail of the first."""
+    import torch
+
+    from ray_b200.comm import B200Comm
+
+    log = []
+
+    class FakeStream:
+        def __init__(self, h):
+            self.cuda_stream = h
+
+        def wait_event(self, ev):
+            log.append(("wait", self.cuda_stream, ev.recorded_on))
+
+    class FakeEvent:
+        def record(self, stream):
+            self.recorded_on = stream.cuda_stream
+
+    cur = {"s": FakeStream(11)}
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: cur["s"])
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    comm = object.__new__(B200Comm)
+    comm.device = 0
+    assert comm._stream() == 11 and log == []          # first op: nothing to order against
+    assert comm._stream() == 11 and log == []          # same stream: free
+    cur["s"] = FakeStream(22)
+    assert comm._stream() == 22 and log == [("wait", 22, 11)]   # switch: 22 waits for the tail of 11
+    assert comm._stream(FakeStream(22)) == 22 and len(log) == 1
+    assert comm._stream(FakeStream(33)) == 33 and log[-1] == ("wait", 33, 22)
+    comm._closed = True  # keep __del__ quiet

@@ -98,3 +98,18 @@ def test_communicator_refuses_cpu_tensors_and_missing_gpu():
 
         with pytest.raises(N.B200Error):
             B200Comm(1, 0, 0, store=DictStore())
+
+
+def test_more_than_eight_workers_fall_back_to_nccl(monkeypatch):
+    """a b200 group is one NVSwitch domain (<= 8 ranks of one host); a larger
+    TorchTrainer must get the reference's default backend instead of failing at the first CUDA op."""
+    import torch.distributed as dist
+
+    from ray_b200.train import torch_config as tc
+
+    seen = {}
+    monkeypatch.setattr(dist, "init_process_group", lambda **kw: seen.update(kw))
+    tc.setup_torch_process_group(tc.DEFAULT_GPU_BACKEND, 0, 16, "env://", timeout_s=5)
+    assert seen["backend"] == "nccl" and seen["world_size"] == 16
+    tc.setup_torch_process_group(tc.DEFAULT_GPU_BACKEND, 0, 8, "env://", timeout_s=5)
+    assert seen["backend"] == tc.DEFAULT_GPU_BACKEND
