@@ -93,11 +93,6 @@ __device__ __forceinline__ void bulk_wait_read() {  // all but the N most recent
 // orders async-proxy accesses (bulk copies) against generic-proxy accesses (ld/st, flags)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-struct BulkTileDesc {
-  const char *src;
-  uint32_t bytes;
-};
-
 // Shared-memory carve-up of a copy CTA (dynamic shared memory, kBulkSmemBytes).
 struct BulkRing {
   uint32_t tiles;  // shared address of tile 0
@@ -117,95 +112,19 @@ __device__ __forceinline__ BulkRing bulk_ring_init(char *dyn_smem) {
   return r;
 }
 
-// Runs the whole tile sequence of one copy role.  Called by exactly one thread.
-//   tile(i)        -> source and length of the i-th tile (pure function of i; called once when the
-//                     load is issued and once when the store is issued)
-//   emit(i, smem, bytes) -> issues the bulk store(s) of tile i from shared address `smem`
-//                     (bulk_s2g; several when the tile goes to several peers)
-//   gate(i, block) -> asked before the LOAD of tile i is issued: 1 = source valid / destination
-//                     free, 0 = not yet (only when !block), -1 = abandon (abort / watchdog).
-//                     The engine first asks without blocking; if the answer is 0 and nothing else
-//                     can make progress it drains its pending stores (so every done() it owes has
-//                     been delivered -- a peer may be waiting for exactly that) and asks again with
-//                     block = true.
-//   done(i)        -> called, in order, once the STORE of tile i has completed (reported lazily:
-//                     when tile i + LAG has been issued, or when the engine drains)
-// Returns false when abandoned.
-// Tile indices are 32-bit on purpose: the callers' index arithmetic (tile -> chunk, offset) then
-// compiles to 32-bit divisions instead of the ~10x slower 64-bit ones, which matters because one
-// thread issues every tile.
-struct BulkNoTrace {
-  __device__ __forceinline__ void operator()(unsigned, unsigned) const {}
-};
-// trace event ids: 1 load issued, 2 load landed + store issued, 3 ring wait passed, 4 done(i)
-// reported, 5 drain (source not ready), 6 blocking gate passed
-template <typename Cfg, typename TileFn, typename EmitFn, typename GateFn, typename DoneFn, typename TraceFn = BulkNoTrace>
-__device__ __forceinline__ bool bulk_copy_run(const BulkRing &ring, uint32_t ntiles, TileFn tile, EmitFn emit,
-                                              GateFn gate, DoneFn done, TraceFn tr = TraceFn()) {
-  constexpr int LAG = Cfg::kLag;
-  constexpr int kBulkLookahead = Cfg::kLookahead;
-  constexpr int kBulkReadPending = kBulkStages - kBulkLookahead - 1;  // stores that may still be reading the ring
-  uint32_t load_i = 0, store_j = 0, completed = 0;
-  bool ok = true;
-  while (store_j < ntiles) {
-    // ring buffer of tile load_i was last used by tile load_i - kBulkStages <= store_j - 1 -
-    // kBulkReadPending, which the wait_group.read below has retired
-    while (load_i < ntiles && load_i - store_j < uint32_t(kBulkLookahead)) {
-      const int g = gate(load_i, false);
-      if (g < 0) ok = false;
-      if (g <= 0) break;
-      const int s = int(load_i % kBulkStages);
-      const BulkTileDesc d = tile(load_i);
-      mbar_expect_tx(ring.bars + 8 * s, d.bytes);
-      bulk_g2s(ring.tiles + uint32_t(s) * kBulkTile, d.src, d.bytes, ring.bars + 8 * s);
-      tr(1, load_i);
-      ++load_i;
-    }
-    if (store_j < load_i) {
-      const int s = int(store_j % kBulkStages);
-      const uint32_t parity = uint32_t(store_j / kBulkStages) & 1u;
-      while (!mbar_try_wait(ring.bars + 8 * s, parity)) {
-      }
-      const BulkTileDesc d = tile(store_j);
-      emit(store_j, ring.tiles + uint32_t(s) * kBulkTile, d.bytes);
-      bulk_commit();
-      tr(2, store_j);
-      ++store_j;
-      bulk_wait_read<kBulkReadPending>();
-      tr(3, store_j);
-      if (completed + LAG < store_j) {
-        bulk_wait<LAG>();
-        for (; completed + LAG < store_j; ++completed) done(completed);
-        tr(4, completed);
-      }
-    } else {
-      // nothing in flight towards shared memory and the next source is not ready
-      tr(5, store_j);
-      bulk_wait<0>();
-      for (; completed < store_j; ++completed) done(completed);
-      if (!ok) break;
-      if (gate(load_i, true) < 0) {
-        ok = false;
-        break;
-      }
-      tr(6, load_i);
-    }
-    if (!ok && store_j == load_i) break;
-  }
-  bulk_wait<0>();
-  for (; completed < store_j; ++completed) done(completed);
-  return ok;
-}
-
 // ---------------------------------------------------------------------------
 // Segment engine.  One thread issues every tile, and a single thread retires a dependent
 // instruction every ~5 cycles, so the per-tile instruction count IS the throughput limit
-// (measured: the index-based engine above, with two divisions and three lambda calls per tile,
+// (measured: a first, index-based engine with two divisions and three lambda calls per tile
 // reached 30-36 GB/s per CTA where the bulk-copy unit does 50).  Here the work is a list of
 // SEGMENTS -- contiguous byte ranges [src, src+bytes) -> [dst, dst+bytes) -- and the tiles of a
 // segment are walked with pointer increments; the callbacks run once per segment, not per tile:
 //   seg(i)         -> BulkSeg of segment i (bytes > 0)
-//   gate(i, block) -> before the first load of segment i (same contract as above)
+//   gate(i, block) -> before the first load of segment i: 1 = source valid / destination free,
+//                     0 = not yet (only when !block), -1 = abandon (abort / watchdog).  The
+//                     engine first asks without blocking; when nothing else can make progress it
+//                     drains its pending stores (every done() it owes has then been delivered -- a
+//                     peer may be waiting for exactly that) and asks again with block = true
 //   done(i)        -> once every store of segment i has completed, in order (lazily, Cfg::kLag tiles)
 // ---------------------------------------------------------------------------
 struct BulkSeg {
