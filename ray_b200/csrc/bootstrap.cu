@@ -950,7 +950,7 @@ void b200_pool_free(void *ptr, size_t size, int device, void *stream) {
 }
 
 const char *b200_last_error(void) { return g_err; }
-const char *b200_version(void) { return "b200_collective 0.1 (sm_100a)"; }
+const char *b200_version(void) { return "b200_collective 0.2 (sm_100a)"; }
 
 size_t b200_dtype_size(int dtype) {
   switch (dtype) {

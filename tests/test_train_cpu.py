@@ -34,6 +34,22 @@ def _worker(rank, world, init_file, out_dir):
     objs = [None] * world
     dist.all_gather_object(objs, {"rank": rank})
     assert [o["rank"] for o in objs] == [0, 1]
+    # rooted and all-to-all ops of the c10d surface: CPU tensors are served by the gloo side
+    mine = torch.full((3,), float(rank + 1))
+    gathered = [torch.zeros(3) for _ in range(world)] if rank == 1 else None
+    dist.gather(mine, gathered, dst=1)
+    if rank == 1:
+        assert [g[0].item() for g in gathered] == [1.0, 2.0]
+    got = torch.zeros(2)
+    dist.scatter(got, [torch.full((2,), 5.0 + p) for p in range(world)] if rank == 0 else None, src=0)
+    assert torch.all(got == 5.0 + rank)
+    src = torch.arange(2 * world, dtype=torch.float32) + 10 * rank
+    dst = torch.zeros(2 * world)
+    dist.all_to_all_single(dst, src)
+    assert dst.tolist() == [2.0 * rank, 2.0 * rank + 1, 10 + 2.0 * rank, 11 + 2.0 * rank]
+    work = dist.all_reduce(torch.ones(2), async_op=True)
+    work.wait()
+    assert work.is_completed()
     dist.barrier()
     # subgroups: rank 0 alone first (rank 1 is not a member), then both -- the second group must
     # still rendezvous although the two ranks have created a different number of groups
