@@ -225,6 +225,13 @@ int b200_comm_set_blocks(b200_comm_t comm, int nblocks);
 int b200_comm_trace_enable(b200_comm_t comm, unsigned int capacity);
 int b200_comm_trace_read(b200_comm_t comm, unsigned long long *out, unsigned int max_events, int reset);
 
+/* Host-side self-test (no GPU needed) of the work decomposition of the pipelined kernels: runs the
+ * very inline functions the kernels use and checks that copy shares tile the message, that the
+ * expected arrival counts match, that reduce work items tile every chunk exactly once and that
+ * ring positions are respected.  0 = consistent; otherwise b200_last_error() says what broke. */
+int b200_selftest_pipe_geometry(size_t nbytes, size_t chunk_bytes, int copy_ctas, int world, int red_ctas,
+                                unsigned ring_chunks);
+
 /* Tuning parameters (must be set identically on every rank; -1 restores the default). */
 typedef enum {
   B200_PARAM_ONESHOT_MAX_BYTES = 0, /* all-reduce messages up to this size use the one-shot kernel */

@@ -100,6 +100,7 @@ SIGNATURES = {
     "b200_comm_launch_count": (c_uint64, [c_void_p]),
     "b200_comm_set_blocks": (c_int, [c_void_p, c_int]),
     "b200_comm_set_param": (c_int, [c_void_p, c_int, ctypes.c_longlong]),
+    "b200_selftest_pipe_geometry": (c_int, [c_size_t, c_size_t, c_int, c_int, c_int, ctypes.c_uint]),
     "b200_comm_trace_enable": (c_int, [c_void_p, ctypes.c_uint]),
     "b200_comm_trace_read": (c_int, [c_void_p, POINTER(ctypes.c_ulonglong), ctypes.c_uint, c_int]),
 }

@@ -31,6 +31,10 @@
 #include "bulk_copy.cuh"
 #include "pipe.h"
 
+#include <algorithm>
+#include <utility>
+#include <vector>
+
 namespace b200 {
 
 struct PipeArgs {
@@ -51,7 +55,7 @@ struct PipeGeom {
   uint32_t share;  // bytes of a full chunk each copy CTA moves: C / G (a multiple of kBulkTile)
   uint32_t R;      // ring length in chunks (0 = no ring)
 };
-__device__ __forceinline__ PipeGeom make_geom(const PipeArgs &a) {
+__host__ __device__ __forceinline__ PipeGeom make_geom(const PipeArgs &a) {
   PipeGeom g;
   g.S = a.nbytes;
   g.C = a.chunk_bytes;
@@ -61,33 +65,33 @@ __device__ __forceinline__ PipeGeom make_geom(const PipeArgs &a) {
   g.R = a.ring_chunks;
   return g;
 }
-__device__ __forceinline__ size_t chunk_len(const PipeGeom &g, uint32_t k) {
+__host__ __device__ __forceinline__ size_t chunk_len(const PipeGeom &g, uint32_t k) {
   const size_t lo = size_t(k) * g.C;
   return (g.S - lo) < g.C ? (g.S - lo) : g.C;
 }
 // Copy CTA j moves bytes [j*share, (j+1)*share) of every chunk (clipped by the message end).
-__device__ __forceinline__ size_t share_off(const PipeGeom &g, uint32_t j, uint32_t k) {
+__host__ __device__ __forceinline__ size_t share_off(const PipeGeom &g, uint32_t j, uint32_t k) {
   return size_t(k) * g.C + size_t(j) * g.share;
 }
 // Where chunk k sits in the staging slot.  With a ring the slot holds R chunks and chunk k reuses
 // the place of chunk k - R, so ONE launch handles a message of any size with R*C bytes of staging:
 // the copy-in of chunk k (share j) waits until the copy-out of chunk k - R (share j) is done, which
 // in turn implies every rank's reducers are done with chunk k - R (they published it).
-__device__ __forceinline__ size_t slot_chunk_off(const PipeGeom &g, uint32_t k) {
+__host__ __device__ __forceinline__ size_t slot_chunk_off(const PipeGeom &g, uint32_t k) {
   return size_t(g.R ? k % g.R : k) * g.C;
 }
-__device__ __forceinline__ uint32_t share_len(const PipeGeom &g, uint32_t j, uint32_t k) {
+__host__ __device__ __forceinline__ uint32_t share_len(const PipeGeom &g, uint32_t j, uint32_t k) {
   const size_t len = chunk_len(g, k), lo = size_t(j) * g.share;
   if (lo >= len) return 0;
   return uint32_t((len - lo) < size_t(g.share) ? (len - lo) : size_t(g.share));
 }
 // chunks in which copy CTA j has bytes: all full chunks, plus the ragged last one if it reaches j's share
-__device__ __forceinline__ uint32_t chunks_of_cta(const PipeGeom &g, uint32_t j) {
+__host__ __device__ __forceinline__ uint32_t chunks_of_cta(const PipeGeom &g, uint32_t j) {
   if (g.K == 0) return 0;
   return share_len(g, j, g.K - 1) ? g.K : g.K - 1;
 }
 // copy CTAs that own bytes of chunk k (= arrivals expected on its counter)
-__device__ __forceinline__ uint32_t copy_arrivals(const PipeGeom &g, uint32_t k) {
+__host__ __device__ __forceinline__ uint32_t copy_arrivals(const PipeGeom &g, uint32_t k) {
   const size_t pieces = (chunk_len(g, k) + g.share - 1) / g.share;
   return uint32_t(pieces < size_t(g.G) ? pieces : size_t(g.G));
 }
@@ -263,9 +267,9 @@ struct ItemIter {
   size_t lo = 0, hi = 0, it = 0;
   uint32_t nitems = 0, cur_k = 0;
   bool in_chunk = false;
-  __device__ ItemIter(const PipeGeom &g_, int r, int n, uint32_t me_, uint32_t Gr_)
+  __host__ __device__ ItemIter(const PipeGeom &g_, int r, int n, uint32_t me_, uint32_t Gr_)
       : g(g_), rank(uint32_t(r)), world(uint32_t(n)), me(me_), Gr(Gr_) {}
-  __device__ bool next(uint32_t &k_out) {
+  __host__ __device__ bool next(uint32_t &k_out) {
     if (in_chunk) {
       it += Gr;
       if (it < nitems) {
@@ -292,7 +296,7 @@ struct ItemIter {
     return false;
   }
   // the scout only has to follow the chunks up to the last one this CTA works on
-  __device__ uint32_t last_chunk_needed() const { return g.K; }
+  __host__ __device__ uint32_t last_chunk_needed() const { return g.K; }
 };
 
 // ---------------------------------------------------------------------------
@@ -938,4 +942,108 @@ int launch_allgather_pull(b200_comm *c, const char *in, char *const *outs, size_
   return B200_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Host-side self-test of the work decomposition (the SAME inline functions the kernels use):
+// every byte of the message is copied in / out by exactly one copy CTA, the arrival counts the
+// flag threads expect are the numbers of CTAs that really own bytes of a chunk, every 16-byte unit
+// of every chunk is reduced by exactly one (rank, reduce CTA, work item), and ring positions of
+// chunks that can be in flight together never overlap.  Runs without a GPU (tests/test_pipe_geometry_cpu.py).
+// ---------------------------------------------------------------------------
+int selftest_pipe_geometry(size_t nbytes, size_t chunk_bytes, int copy_ctas, int world, int red_ctas,
+                           unsigned ring_chunks) {
+  if (nbytes == 0 || (nbytes & 15) || chunk_bytes == 0 || chunk_bytes % (size_t(copy_ctas) * kBulkTile) || copy_ctas < 1 ||
+      world < 2 || world > kMaxRanks || red_ctas < 1) {
+    set_error("invalid self-test arguments");
+    return B200_ERR_INVALID;
+  }
+  PipeArgs a{nullptr, nullptr, nbytes, 0, chunk_bytes, copy_ctas, ring_chunks};
+  const PipeGeom g = make_geom(a);
+  // ---- copy roles --------------------------------------------------------------------------
+  std::vector<std::pair<size_t, size_t>> iv;  // [begin, end)
+  std::vector<uint32_t> owners(g.K, 0);
+  for (uint32_t j = 0; j < g.G; ++j) {
+    const uint32_t nc = chunks_of_cta(g, j);
+    for (uint32_t k = 0; k < g.K; ++k) {
+      const uint32_t len = share_len(g, j, k);
+      if ((k < nc) != (len > 0)) {
+        set_error("copy CTA %u: chunks_of_cta=%u disagrees with share_len of chunk %u", j, nc, k);
+        return B200_ERR_INVALID;
+      }
+      if (!len) continue;
+      if (len & 15) {
+        set_error("share of CTA %u in chunk %u is not a multiple of 16 bytes", j, k);
+        return B200_ERR_INVALID;
+      }
+      ++owners[k];
+      iv.emplace_back(share_off(g, j, k), share_off(g, j, k) + len);
+      if (g.R) {  // the share must stay inside the ring position of its chunk
+        const size_t pos = slot_chunk_off(g, k) + size_t(j) * g.share;
+        if (pos + len > size_t(g.R) * g.C || pos / g.C != k % g.R) {
+          set_error("ring placement of chunk %u share %u leaves its position", k, j);
+          return B200_ERR_INVALID;
+        }
+      }
+    }
+  }
+  std::sort(iv.begin(), iv.end());
+  size_t at = 0;
+  for (auto &e : iv) {
+    if (e.first != at) {
+      set_error("copy shares do not tile the message at byte %zu (next share starts at %zu)", at, e.first);
+      return B200_ERR_INVALID;
+    }
+    at = e.second;
+  }
+  if (at != nbytes) {
+    set_error("copy shares end at %zu, message has %zu bytes", at, nbytes);
+    return B200_ERR_INVALID;
+  }
+  for (uint32_t k = 0; k < g.K; ++k)
+    if (owners[k] != copy_arrivals(g, k)) {
+      set_error("chunk %u: %u copy CTAs own bytes, flag thread expects %u arrivals", k, owners[k], copy_arrivals(g, k));
+      return B200_ERR_INVALID;
+    }
+  // ---- reduce role ---------------------------------------------------------------------------
+  std::vector<std::pair<size_t, size_t>> units;  // global 16-byte unit ranges
+  for (int r = 0; r < world; ++r) {
+    std::vector<uint32_t> items(g.K, 0), expect(g.K, 0);
+    for (int me = 0; me < red_ctas; ++me) {
+      ItemIter iter(g, r, world, uint32_t(me), uint32_t(red_ctas));
+      uint32_t k = 0;
+      while (iter.next(k)) {
+        ++items[k];
+        expect[k] = iter.nitems;
+        const size_t base = (size_t(k) * g.C) >> 4;
+        const size_t lo = iter.lo + iter.it * kItemUnits;
+        const size_t hi = lo + kItemUnits < iter.hi ? lo + kItemUnits : iter.hi;
+        if (lo < hi) units.emplace_back(base + lo, base + hi);
+      }
+    }
+    for (uint32_t k = 0; k < g.K; ++k)
+      if (items[k] != expect[k] || items[k] == 0) {
+        set_error("rank %d chunk %u: %u work items dealt, arrival thread expects %u", r, k, items[k], expect[k]);
+        return B200_ERR_INVALID;
+      }
+  }
+  std::sort(units.begin(), units.end());
+  at = 0;
+  for (auto &e : units) {
+    if (e.first != at) {
+      set_error("reduce items do not tile the message at unit %zu (next item starts at %zu)", at, e.first);
+      return B200_ERR_INVALID;
+    }
+    at = e.second;
+  }
+  if (at != (nbytes >> 4)) {
+    set_error("reduce items end at unit %zu, message has %zu units", at, nbytes >> 4);
+    return B200_ERR_INVALID;
+  }
+  return B200_OK;
+}
+
 }  // namespace b200
+
+extern "C" int b200_selftest_pipe_geometry(size_t nbytes, size_t chunk_bytes, int copy_ctas, int world, int red_ctas,
+                                           unsigned ring_chunks) {
+  return b200::selftest_pipe_geometry(nbytes, chunk_bytes, copy_ctas, world, red_ctas, ring_chunks);
+}
